@@ -1,0 +1,148 @@
+/* libk5 — C ABI of the B200-native Kandinsky-5 DiT denoising engine.
+ *
+ * The reference (ai-forever/Kandinsky-5) is pure Python and has no FFI of its own; these entry points are
+ * what a binding for its hot path replaces (all citations relative to the reference tree):
+ *
+ *   k5_engine_create / k5_engine_load_tensor / k5_engine_finalize
+ *        <- get_dit(conf.model.dit_params) + dit.load_state_dict(load_file(ckpt), assign=True)
+ *           kandinsky/utils.py:105,115-116 ; kandinsky/models/dit.py:82-127,184-186
+ *   k5_engine_set_grid
+ *        <- RoPE3D.forward + fractal_flatten set-up, kandinsky/models/dit.py:140-147, nn.py:132-150
+ *   k5_dit_forward
+ *        <- DiffusionTransformer3D.forward, kandinsky/models/dit.py:155-181
+ *   k5_sample
+ *        <- generate() / get_velocity(), kandinsky/generation_utils.py:39-129
+ *   k5_gemm_bf16, k5_attention, k5_ln_rows, k5_nabla_*      (operator level; used by the parity tests)
+ *        <- nn.Linear call sites nn.py:181-184,206,235-237,284,317-319,341,354-361,376-382;
+ *           flash_attn_func nn.py:201,254,336; apply_scale_shift_norm nn.py:25-28;
+ *           nablaT_v2 models/utils.py:136-163 + flex_attention nn.py:257-280
+ *
+ * Conventions
+ *   - every data pointer is CALLER-OWNED DEVICE memory unless the parameter name ends in _host;
+ *     the engine never frees caller memory and owns its weights / workspace;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous with
+ *     respect to the host except create / load_tensor / finalize / set_grid;
+ *   - return value 0 = success; non-zero = error code, message via k5_last_error() (thread local).
+ *     The Python binding maps K5_ERR_INVALID to ValueError and the rest to RuntimeError, mirroring the
+ *     reference's exceptions;
+ *   - one engine per GPU per process, not re-entrant (the reference drives one model per rank from a
+ *     single Python thread, README.md:271-276);
+ *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16.
+ */
+#ifndef K5_H
+#define K5_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define K5_OK 0
+#define K5_ERR_INVALID 1
+#define K5_ERR_CUDA 2
+#define K5_ERR_STATE 3
+#define K5_ERR_UNSUPPORTED 4
+
+typedef struct k5_engine k5_engine;
+
+/* Mirrors conf.model.dit_params (configs/config_5s_sft.yaml:11-29) plus workspace bounds. */
+typedef struct k5_config {
+    int32_t in_visual_dim;     /* latent channels (16) */
+    int32_t out_visual_dim;    /* 16 */
+    int32_t time_dim;          /* 512 */
+    int32_t patch_size[3];     /* (1,2,2) — the only patching the engine supports */
+    int32_t model_dim;         /* 1792 */
+    int32_t ff_dim;            /* 7168 */
+    int32_t num_text_blocks;   /* 2 */
+    int32_t num_visual_blocks; /* 32 */
+    int32_t axes_dims[3];      /* (16,24,24): must sum to head_dim 64 */
+    int32_t visual_cond;       /* 1: input has 2*in_visual_dim+1 channels */
+    int32_t in_text_dim;       /* 3584 */
+    int32_t in_text_dim2;      /* 768 */
+    int32_t max_tokens;        /* workspace bound on visual tokens S (47616 for 5 s, 93696 for 10 s) */
+    int32_t max_text_tokens;   /* workspace bound on text tokens L (<= 1024) */
+} k5_config;
+
+/* NABLA sparse attention parameters (generation_utils.py:10-36; models/utils.py:108-163). */
+typedef struct k5_sparse {
+    float P;                   /* cumulative-probability threshold (conf.model.attention.P) */
+    int32_t wT, wH, wW;        /* STA window over the 64-token block grid */
+    int32_t add_sta;           /* OR the STA mask into the adaptive mask (the reference always does) */
+} k5_sparse;
+
+const char* k5_last_error(void);
+int k5_version(void);
+
+int k5_engine_create(const k5_config* cfg, k5_engine** out);
+void k5_engine_destroy(k5_engine* e);
+
+/* One call per state-dict entry, keys exactly as in the reference checkpoint, plus the
+ * reference's non-persistent buffers: "time_embeddings.freqs", "text_rope_embeddings.args",
+ * "visual_rope_embeddings.args_{0,1,2}".  `data` may be host or device memory. The engine converts and
+ * repacks (fused QKV, bf16 GEMM operands, fp32 norm / modulation / time-MLP tensors) into its own storage. */
+int k5_engine_load_tensor(k5_engine* e, const char* key, const void* data, int dtype, const int64_t* shape, int ndim);
+/* Fails with K5_ERR_STATE (message lists them) if any tensor of the contract was not loaded. */
+int k5_engine_finalize(k5_engine* e);
+
+/* Latent grid [T, H, W] (H, W in latent pixels, i.e. before 2x2 patching), RoPE positions (host arrays of
+ * length T, H/2, W/2; NULL = arange), RoPE scale_factor (conf.metrics.scale_factor) and token order
+ * (fractal = 1 is the NABLA order, needs H/2 and W/2 divisible by 8). */
+int k5_engine_set_grid(k5_engine* e, int T, int H, int W, const int32_t* pos_t_host, const int32_t* pos_h_host,
+                       const int32_t* pos_w_host, const float scale_factor[3], int fractal);
+
+/* One DiT forward.  x: float32 [T,H,W,Cx] with Cx = in channels of the model (33) or Cx = in_visual_dim
+ * (then the zero visual-cond / mask channels are implied); text: bf16 [L, in_text_dim]; pooled: bf16
+ * [in_text_dim2]; time = t * 1000; text_pos_host: L positions or NULL = arange; sparse: NULL = dense
+ * attention; out: bf16 [T,H,W,out_visual_dim]. */
+int k5_dit_forward(k5_engine* e, const float* x, int Cx, const void* text, int L, const int32_t* text_pos_host,
+                   const void* pooled, float time, const k5_sparse* sparse, void* out, void* stream);
+
+/* The whole flow-matching Euler loop on the device.  img: float32 [T,H,W,in_visual_dim], noise in / latent
+ * out (updated in place).  null_text / null_pooled may be NULL when |guidance_weight - 1| <= 1e-6. */
+int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, float scheduler_scale, const void* text,
+              int L, const void* pooled, const void* null_text, int Ln, const void* null_pooled, const k5_sparse* sparse,
+              void* stream);
+
+/* Number of kernels launched by this library since the counter was last reset (bench.py's gpu_launches). */
+int64_t k5_launch_count(int reset);
+
+/* Realised NABLA block density of the last sparse forward (selected / total 64x64 blocks, averaged over
+ * blocks and heads); 1.0 if the last forward was dense.  Synchronises the stream it was produced on. */
+float k5_last_sparse_density(k5_engine* e);
+
+/* ---- operator level ---------------------------------------------------------------------------------- */
+#define K5_EPI_STORE 0
+#define K5_EPI_GELU 1
+#define K5_EPI_GATE 2
+#define K5_EPI_HEADS 3
+
+/* out[M,N] = epilogue(A[M,K] . W[N,K]^T); A, W, out, resid bf16; bias, gate, norm weights float32;
+ * rope: float2 [M,32] (cos,sin).  See csrc/gemm.h for the epilogue semantics. */
+int k5_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue, void* out, int ldo,
+                 const float* bias, const void* resid, int ldr, const float* gate, const float* norm_w0,
+                 const float* norm_w1, int norm_split, int norm_cols, int rope_cols, const void* rope, void* stream);
+
+/* O = softmax(Q K^T * scale) V, head_dim 64, non-causal; head h = columns [64h, 64h+64) of each matrix.
+ * kv_count / kv_index: optional block-sparse lists over 64x64 blocks: int32 [heads, Sq/64] and
+ * [heads, Sq/64, Sk/64] (first kv_count entries valid), NULL = dense. */
+int k5_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq, int Sk,
+                 int heads, float scale, const int32_t* kv_count, const int32_t* kv_index, void* stream);
+
+/* out = bf16(LN(x) * (mul + plus_one) + add), fp32 statistics, eps; x, out bf16 [S,D]; mul, add float32 [D]. */
+int k5_ln_rows(const void* x, int ldx, void* out, int ldo, int S, int D, const float* mul, const float* add, int plus_one,
+               float eps, void* stream);
+
+/* NABLA block selection (nablaT_v2): q, k bf16 [S, heads*64] (post-norm, post-RoPE, fractal order) ->
+ * kv_count int32 [heads, S/64], kv_index int32 [heads, S/64, S/64] (ascending block ids).
+ * sta: uint8 [S/64, S/64] or NULL.  workspace: float32 [heads * (S/64)^2 + 2 * S/64 * heads * 64]. */
+int k5_nabla_select(const void* q, int ldq, const void* k, int ldk, int S, int heads, float P, const uint8_t* sta,
+                    int32_t* kv_count, int32_t* kv_index, float* workspace, void* stream);
+/* STA block mask (fast_sta_nabla): uint8 [T*Hb*Wb, T*Hb*Wb], row-major (t,h,w) block order. */
+int k5_sta_mask(int T, int Hb, int Wb, int wT, int wH, int wW, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* K5_H */

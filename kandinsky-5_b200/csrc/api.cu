@@ -1,0 +1,148 @@
+// extern "C" surface of libk5 (include/k5.h): plain pointers and sizes only.
+#include "../../include/k5.h"
+#include "attention.h"
+#include "common.h"
+#include "gemm.h"
+#include "nabla.h"
+#include "rowops.h"
+
+namespace k5 {
+struct Engine;
+Engine* engine_new(const k5_config* cfg, int* rc);
+void engine_delete(Engine* e);
+int engine_load_tensor(Engine* e, const char* key, const void* data, int dtype, const int64_t* shape, int ndim);
+int engine_finalize(Engine* e);
+int engine_set_grid(Engine* e, int T, int H, int W, const int32_t* pt, const int32_t* ph, const int32_t* pw,
+                    const float sf[3], int fractal);
+int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, const int32_t* text_pos, const bf16* pooled,
+                   float time, const k5_sparse* sp, bf16* out, cudaStream_t st);
+int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, const bf16* text, int L, const bf16* pooled,
+                  const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st);
+float engine_density(Engine* e);
+int64_t launch_count(bool reset);
+void count_launch(int n);
+}  // namespace k5
+
+using namespace k5;
+
+#define K5_NEED(p)                                         \
+    do {                                                   \
+        if (!(p)) {                                        \
+            set_last_error("null argument: " #p);          \
+            return K5_ERR_INVALID;                         \
+        }                                                  \
+    } while (0)
+
+extern "C" {
+
+const char* k5_last_error(void) { return get_last_error(); }
+int k5_version(void) { return 100; }
+
+int k5_engine_create(const k5_config* cfg, k5_engine** out) {
+    K5_NEED(cfg);
+    K5_NEED(out);
+    int rc = 0;
+    Engine* e = engine_new(cfg, &rc);
+    *out = reinterpret_cast<k5_engine*>(e);
+    return rc;
+}
+void k5_engine_destroy(k5_engine* e) {
+    if (e) engine_delete(reinterpret_cast<Engine*>(e));
+}
+int k5_engine_load_tensor(k5_engine* e, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+    K5_NEED(e);
+    return engine_load_tensor(reinterpret_cast<Engine*>(e), key, data, dtype, shape, ndim);
+}
+int k5_engine_finalize(k5_engine* e) {
+    K5_NEED(e);
+    return engine_finalize(reinterpret_cast<Engine*>(e));
+}
+int k5_engine_set_grid(k5_engine* e, int T, int H, int W, const int32_t* pt, const int32_t* ph, const int32_t* pw,
+                       const float scale_factor[3], int fractal) {
+    K5_NEED(e);
+    return engine_set_grid(reinterpret_cast<Engine*>(e), T, H, W, pt, ph, pw, scale_factor, fractal);
+}
+int k5_dit_forward(k5_engine* e, const float* x, int Cx, const void* text, int L, const int32_t* text_pos_host,
+                   const void* pooled, float time, const k5_sparse* sparse, void* out, void* stream) {
+    K5_NEED(e);
+    return engine_forward(reinterpret_cast<Engine*>(e), x, Cx, static_cast<const bf16*>(text), L, text_pos_host,
+                          static_cast<const bf16*>(pooled), time, sparse, static_cast<bf16*>(out),
+                          static_cast<cudaStream_t>(stream));
+}
+int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, float scheduler_scale, const void* text, int L,
+              const void* pooled, const void* null_text, int Ln, const void* null_pooled, const k5_sparse* sparse,
+              void* stream) {
+    K5_NEED(e);
+    return engine_sample(reinterpret_cast<Engine*>(e), img, num_steps, guidance_weight, scheduler_scale,
+                         static_cast<const bf16*>(text), L, static_cast<const bf16*>(pooled),
+                         static_cast<const bf16*>(null_text), Ln, static_cast<const bf16*>(null_pooled), sparse,
+                         static_cast<cudaStream_t>(stream));
+}
+int64_t k5_launch_count(int reset) { return launch_count(reset != 0); }
+float k5_last_sparse_density(k5_engine* e) { return e ? engine_density(reinterpret_cast<Engine*>(e)) : 1.0f; }
+
+int k5_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue, void* out, int ldo,
+                 const float* bias, const void* resid, int ldr, const float* gate, const float* norm_w0,
+                 const float* norm_w1, int norm_split, int norm_cols, int rope_cols, const void* rope, void* stream) {
+    K5_NEED(A);
+    K5_NEED(W);
+    K5_NEED(out);
+    GemmEpilogue e;
+    e.out = static_cast<bf16*>(out);
+    e.ldo = ldo;
+    e.bias = bias;
+    e.resid = static_cast<const bf16*>(resid);
+    e.ldr = ldr;
+    e.gate = gate;
+    e.norm_w0 = norm_w0;
+    e.norm_w1 = norm_w1;
+    e.norm_split = norm_split;
+    e.norm_cols = norm_cols;
+    e.rope_cols = rope_cols;
+    e.rope = static_cast<const float2*>(rope);
+    count_launch(1);
+    return gemm_bf16(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, M, N, K, epilogue, e,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int k5_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq, int Sk,
+                 int heads, float scale, const int32_t* kv_count, const int32_t* kv_index, void* stream) {
+    K5_NEED(Q);
+    K5_NEED(K);
+    K5_NEED(V);
+    K5_NEED(O);
+    count_launch(1);
+    return attention_fwd(static_cast<const bf16*>(Q), ldq, static_cast<const bf16*>(K), ldk, static_cast<const bf16*>(V),
+                         ldv, static_cast<bf16*>(O), ldo, Sq, Sk, heads, scale, kv_count, kv_index,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int k5_ln_rows(const void* x, int ldx, void* out, int ldo, int S, int D, const float* mul, const float* add, int plus_one,
+               float eps, void* stream) {
+    K5_NEED(x);
+    K5_NEED(out);
+    K5_NEED(mul);
+    K5_NEED(add);
+    count_launch(1);
+    return ln_rows(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(out), ldo, S, D, mul, add, plus_one != 0, eps,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int k5_nabla_select(const void* q, int ldq, const void* k, int ldk, int S, int heads, float P, const uint8_t* sta,
+                    int32_t* kv_count, int32_t* kv_index, float* workspace, void* stream) {
+    K5_NEED(q);
+    K5_NEED(k);
+    K5_NEED(kv_count);
+    K5_NEED(kv_index);
+    K5_NEED(workspace);
+    count_launch(nabla_select_launches());
+    return nabla_select(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, S, heads, P, sta, kv_count,
+                        kv_index, workspace, nullptr, static_cast<cudaStream_t>(stream));
+}
+int k5_sta_mask(int T, int Hb, int Wb, int wT, int wH, int wW, uint8_t* out, void* stream) {
+    K5_NEED(out);
+    count_launch(1);
+    return sta_mask(T, Hb, Wb, wT, wH, wW, out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

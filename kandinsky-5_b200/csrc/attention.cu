@@ -1,0 +1,346 @@
+// Non-causal multi-head attention forward for head_dim 64 on tcgen05 / TMEM:  O = softmax(Q K^T * scale) V.
+//
+// Replaces flash_attn_func at kandinsky/models/nn.py:201,254,336 (visual self-attention, cross-attention
+// to the text tokens, text self-attention) and, with a per-(head, q-block) KV block list,
+// flex_attention at nn.py:257-280 (NABLA, K2).  bf16 in / out, fp32 scores, softmax and accumulation.
+//
+// One persistent CTA per SM works on (head, 256-query-row) items, heads outermost so that the K/V of
+// one head (12 MB at S = 47 616) stay L2 resident while all CTAs sweep its query tiles.  Roles:
+//   warps 0-3 / 4-7 : softmax warpgroups for query tile 0 / 1 (thread = one query row, so row max / sum
+//                     need no shuffles); they read S from TMEM, write P = exp2(.) back to TMEM as bf16
+//                     (aliasing S), rescale O lazily (only when the running max grew by > 2^8), and
+//                     normalise + store O at the end;
+//   warp 8          : TMA producer (Q tiles once per item, K and V tiles through a 5-stage ring);
+//   warp 9          : tcgen05.mma issuer:  S_a = Q_a K_j^T (SS form, 128x128x64), O_a += P_a V_j
+//                     (TS form: A = P from TMEM, B = V MN-major from shared memory, 128x64x128);
+//   warp 10         : TMEM allocation (S0 S1 O0 O1 = 384 of 512 columns).
+// The two query tiles ping-pong: while one warpgroup does its exponentials the tensor pipe serves the
+// other, because the issue order is  PV_a(j), QK_a(j+1)  per tile a (the pipe executes in order, which
+// is also what makes aliasing P onto S safe).
+#include "attention.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace k5 {
+
+namespace {
+
+constexpr int QT = 128;            // query rows per tile (2 tiles per CTA item)
+constexpr int KT = 128;            // kv rows per tile
+constexpr int HD = 64;             // head dim
+constexpr int TILE_BYTES = 128 * 64 * 2;
+constexpr int KV_STAGES = 5;
+constexpr int ATT_SMEM = 2 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + 1024 + 512;
+constexpr int ATT_THREADS = 384;
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: P stays <= 2^8 before a rescale is forced
+
+struct Bars {
+    uint64_t q_full[2], q_empty[2];
+    uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
+    uint64_t s_full[2], p_ready[2], pv_done[2], o_free[2];
+    uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                  // 2 tiles
+    uint8_t* sKV = smem + 2 * TILE_BYTES;                // stage s: K at s*2*TILE, V at +TILE
+    Bars* B = reinterpret_cast<Bars*>(smem + 2 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const int n_qpairs = (p.Sq + 2 * QT - 1) / (2 * QT);
+    const int n_items = n_qpairs * p.heads;
+    const int nkv = (p.Sk + KT - 1) / KT;
+    const int kv_rem = p.Sk - (nkv - 1) * KT;           // valid kv rows in the last tile (1..128)
+
+    if (warp == 8 && elect_one()) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 9 && elect_one()) {
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&B->q_full[a], 1);
+            mbar_init(&B->q_empty[a], 1);
+            mbar_init(&B->s_full[a], 1);
+            mbar_init(&B->p_ready[a], 128);
+            mbar_init(&B->pv_done[a], 1);
+            mbar_init(&B->o_free[a], 128);
+        }
+        for (int s = 0; s < KV_STAGES; ++s) {
+            mbar_init(&B->k_full[s], 1);
+            mbar_init(&B->k_empty[s], 1);
+            mbar_init(&B->v_full[s], 1);
+            mbar_init(&B->v_empty[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 10) tmem_alloc<512>(&B->tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = B->tmem_slot;
+
+    if (warp >= 8) {
+        reg_dec<56>();
+        if (warp == 8) {
+            // ===================== TMA producer =====================
+            if (elect_one()) {
+                int st = 0;
+                uint32_t ph = 0;
+                int i = 0;
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+                    const int h = item / n_qpairs;
+                    const int q0 = (item % n_qpairs) * 2 * QT;
+                    for (int a = 0; a < 2; ++a) {
+                        mbar_wait(&B->q_empty[a], (i & 1) ^ 1);
+                        mbar_expect_tx(&B->q_full[a], TILE_BYTES);
+                        tma_load_2d(sQ + a * TILE_BYTES, &tmQ, &B->q_full[a], h * HD, q0 + a * QT);
+                    }
+                    for (int j = 0; j < nkv; ++j) {
+                        uint8_t* sk = sKV + st * 2 * TILE_BYTES;
+                        mbar_wait(&B->k_empty[st], ph ^ 1);
+                        mbar_expect_tx(&B->k_full[st], TILE_BYTES);
+                        tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, j * KT);
+                        mbar_wait(&B->v_empty[st], ph ^ 1);
+                        mbar_expect_tx(&B->v_full[st], TILE_BYTES);
+                        tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, j * KT);
+                        if (++st == KV_STAGES) {
+                            st = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == 9) {
+            // ===================== MMA issuer =====================
+            if (elect_one()) {
+                constexpr uint32_t idesc_qk = umma_idesc_bf16(QT, KT, 0, 0);
+                constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);
+                const uint32_t tS[2] = {tmem_base + TM_S0, tmem_base + TM_S1};
+                const uint32_t tO[2] = {tmem_base + TM_O0, tmem_base + TM_O1};
+                const uint32_t sq_addr = smem_u32(sQ);
+                const uint32_t skv_addr = smem_u32(sKV);
+                int kst = 0, vst = 0;
+                uint32_t kph = 0, vph = 0;
+                uint32_t cnt = 0;           // kv tiles processed so far (same for both query tiles)
+                int i = 0;
+
+                auto issue_qk = [&](int a, int stage) {
+                    const uint32_t qa = sq_addr + a * TILE_BYTES;
+                    const uint32_t ka = skv_addr + stage * 2 * TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_ss(tS[a], umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024),
+                                idesc_qk, k != 0 ? 1u : 0u);
+                    umma_commit(&B->s_full[a]);
+                };
+                auto issue_pv = [&](int a, int stage, bool accumulate) {
+                    const uint32_t va = skv_addr + stage * 2 * TILE_BYTES + TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KT / 16; ++k)
+                        umma_ts(tO[a], tS[a] + k * 8, umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
+                                (accumulate || k != 0) ? 1u : 0u);
+                    umma_commit(&B->pv_done[a]);
+                };
+
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+                    // S_a(0) = Q_a K_0^T
+                    mbar_wait(&B->k_full[kst], kph);
+                    for (int a = 0; a < 2; ++a) {
+                        mbar_wait(&B->q_full[a], i & 1);
+                        tc_fence_after();
+                        issue_qk(a, kst);
+                    }
+                    umma_commit(&B->k_empty[kst]);
+                    if (++kst == KV_STAGES) {
+                        kst = 0;
+                        kph ^= 1;
+                    }
+                    for (int j = 0; j < nkv; ++j, ++cnt) {
+                        mbar_wait(&B->v_full[vst], vph);
+                        for (int a = 0; a < 2; ++a) {
+                            if (j == 0) mbar_wait(&B->o_free[a], (i & 1) ^ 1);
+                            mbar_wait(&B->p_ready[a], cnt & 1);
+                            tc_fence_after();
+                            issue_pv(a, vst, j != 0);
+                            if (j + 1 < nkv) {
+                                if (a == 0) {
+                                    mbar_wait(&B->k_full[kst], kph);
+                                    tc_fence_after();
+                                }
+                                issue_qk(a, kst);
+                                if (a == 1) {
+                                    umma_commit(&B->k_empty[kst]);
+                                    if (++kst == KV_STAGES) {
+                                        kst = 0;
+                                        kph ^= 1;
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit(&B->v_empty[vst]);
+                        if (++vst == KV_STAGES) {
+                            vst = 0;
+                            vph ^= 1;
+                        }
+                    }
+                    umma_commit(&B->q_empty[0]);
+                    umma_commit(&B->q_empty[1]);
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warpgroups =====================
+        reg_inc<224>();
+        const int a = warp >> 2;                          // query tile of this warpgroup
+        const int wq = warp & 3;
+        const int lane = threadIdx.x & 31;
+        const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+        const uint32_t tS = tmem_base + (a == 0 ? TM_S0 : TM_S1) + lane_off;
+        const uint32_t tO = tmem_base + (a == 0 ? TM_O0 : TM_O1) + lane_off;
+        const float sl2 = p.scale_log2;
+        uint32_t cnt = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int h = item / n_qpairs;
+            const int row = (item % n_qpairs) * 2 * QT + a * QT + wq * 32 + lane;
+            float m_used = -INFINITY;
+            float l = 0.f;
+            for (int j = 0; j < nkv; ++j, ++cnt) {
+                mbar_wait(&B->s_full[a], cnt & 1);
+                tc_fence_after();
+                uint32_t s[128];
+                tmem_ld32(tS + 0, s);
+                tmem_ld32(tS + 32, s + 32);
+                tmem_ld32(tS + 64, s + 64);
+                tmem_ld32(tS + 96, s + 96);
+                tmem_wait_ld();
+                if (j == nkv - 1 && kv_rem < KT) {
+#pragma unroll
+                    for (int c = 0; c < 128; ++c)
+                        if (c >= kv_rem) s[c] = 0xff800000u;      // -inf
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 128; c += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+                    mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                float alpha = 1.0f;
+                bool need = false;
+                if (j == 0) {
+                    m_used = mx;
+                } else if ((mx - m_used) * sl2 > RESCALE_THRESHOLD) {
+                    alpha = fast_exp2((m_used - mx) * sl2);
+                    m_used = mx;
+                    need = true;
+                }
+                const float mneg = -m_used * sl2;
+                float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), sl2, mneg));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), sl2, mneg));
+                    sum0 += p0;
+                    sum1 += p1;
+                    s[c] = pack_bf16x2(p0, p1);              // P packed in place (c <= 2c)
+                }
+                l = l * alpha + (sum0 + sum1);
+                tmem_st32(tS + 0, s);
+                tmem_st32(tS + 32, s + 32);
+                tmem_wait_st();
+                if (j > 0 && __any_sync(0xffffffffu, need)) {
+                    // O_a holds the sum over tiles < j: wait for PV_a(j-1), then rescale this warp's rows.
+                    mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
+                    tc_fence_after();
+                    uint32_t o[64];
+                    tmem_ld32(tO, o);
+                    tmem_ld32(tO + 32, o + 32);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                    tmem_st32(tO, o);
+                    tmem_st32(tO + 32, o + 32);
+                    tmem_wait_st();
+                }
+                tc_fence_before();
+                mbar_arrive(&B->p_ready[a]);
+            }
+            // ---- epilogue: O_a / l -> bf16 -> global
+            mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
+            tc_fence_after();
+            uint32_t o[64];
+            tmem_ld32(tO, o);
+            tmem_ld32(tO + 32, o + 32);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&B->o_free[a]);
+            if (row < p.Sq) {
+                const float inv = 1.0f / l;
+                uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.ldo + h * HD);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 v;
+                    v.x = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+                    v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+                    v.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+                    v.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+                    dst[c] = v;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 10) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+
+int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
+                  int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
+                  cudaStream_t st) {
+    K5_REQUIRE(Sq > 0 && Sk > 0 && heads > 0, "attention: empty problem");
+    if (kv_count || kv_index) {
+        set_last_error("attention: block-sparse KV lists are not implemented yet");
+        return K5_ERR_UNSUPPORTED;
+    }
+    K5_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: pitches must be x8 elements");
+    K5_REQUIRE((reinterpret_cast<uintptr_t>(O) & 15) == 0, "attention: output must be 16-byte aligned");
+    CUtensorMap tmQ, tmK, tmV;
+    K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
+    K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
+    K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
+    static bool configured = false;
+    if (!configured) {
+        K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        configured = true;
+    }
+    AttnParams p;
+    p.Sq = Sq;
+    p.Sk = Sk;
+    p.heads = heads;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.out = O;
+    p.ldo = ldo;
+    p.kv_count = kv_count;
+    p.kv_index = kv_index;
+    const int n_items = ((Sq + 2 * QT - 1) / (2 * QT)) * heads;
+    const int grid = n_items < sm_count() ? n_items : sm_count();
+    attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    K5_CHECK_CUDA(cudaGetLastError());
+    return K5_OK;
+}
+
+}  // namespace k5

@@ -1,0 +1,694 @@
+// The DiT denoising engine behind the C ABI (include/k5.h): owns repacked weights and workspace, runs
+// DiffusionTransformer3D.forward (kandinsky/models/dit.py:155-181) and the flow-matching sampler
+// (kandinsky/generation_utils.py:39-129) as a fixed sequence of the kernels in gemm.cu / attention.cu /
+// rowops.cu / nabla.cu on one stream.  No host synchronisation inside forward / sample.
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/k5.h"
+#include "attention.h"
+#include "common.h"
+#include "gemm.h"
+#include "nabla.h"
+#include "rowops.h"
+
+namespace k5 {
+
+static int64_t g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+int64_t launch_count(bool reset) {
+    int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+namespace {
+
+constexpr float LN_EPS = 1e-5f;
+
+struct Lin {
+    bf16* W = nullptr;     // [out, ld] bf16
+    float* b = nullptr;    // [out] fp32 (bf16-rounded) or null
+    int out = 0, in = 0, ld = 0;
+};
+struct AttnW {
+    Lin qkv;               // self: [3D, D];  cross: q [D, D]
+    Lin kv;                // cross only: [2D, D]
+    Lin o;
+    float *qn = nullptr, *kn = nullptr;   // [64]
+};
+struct Block {
+    size_t mod_off = 0;    // row offset into the concatenated modulation output
+    AttnW self, cross;
+    Lin ff_in, ff_out;
+};
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+    K5_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    return K5_OK;
+}
+
+}  // namespace
+
+struct Engine {
+    k5_config c{};
+    int D = 0, F = 0, Td = 0, heads = 0, Cin = 0, KP = 0;
+    size_t mod_rows = 0;
+    std::vector<void*> allocs;
+    std::set<std::string> expected, loaded;
+
+    // weights
+    float *modW = nullptr, *modB = nullptr;
+    Lin time_in_dummy;
+    float *time_in_W = nullptr, *time_in_b = nullptr, *time_out_W = nullptr, *time_out_b = nullptr;
+    Lin text_in, vis_in, out_lin, pooled_in;
+    float *text_ln_w = nullptr, *text_ln_b = nullptr, *pooled_ln_w = nullptr, *pooled_ln_b = nullptr;
+    std::vector<Block> tblocks, vblocks;
+    size_t out_mod_off = 0;
+    float *freqs = nullptr, *args_text = nullptr, *args_ax[3] = {nullptr, nullptr, nullptr};
+
+    // workspace
+    bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *patchA = nullptr, *y64 = nullptr;
+    bf16 *te = nullptr, *ten = nullptr, *tqkv = nullptr, *tatt = nullptr, *thid = nullptr, *tproj = nullptr, *ckv = nullptr;
+    float *tfeat = nullptr, *t1 = nullptr, *tembed = nullptr, *modOut = nullptr;
+    float2 *rope_v = nullptr, *rope_t = nullptr, *rope_t_arange = nullptr;
+    int *pos_dev = nullptr;         // [T + Hp + Wp] then text positions at +4096
+    bf16 *v_c = nullptr, *v_u = nullptr;
+    // NABLA
+    uint8_t* sta = nullptr;
+    int32_t *kv_count = nullptr, *kv_index = nullptr;
+    float* nabla_ws = nullptr;
+    float* density_acc = nullptr;
+    int sta_key[6] = {0, 0, 0, 0, 0, 0};
+    bool last_sparse = false;
+    cudaStream_t last_stream = nullptr;
+
+    // staging for load_tensor
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+
+    // grid
+    int T = 0, Hp = 0, Wp = 0, S = 0, fractal = 0;
+    bool grid_set = false;
+    bool finalized = false;
+
+    template <typename T_>
+    int alloc(T_** p, size_t n) {
+        K5_TRY(dalloc(p, n));
+        allocs.push_back(*p);
+        return K5_OK;
+    }
+    int alloc_lin(Lin& l, int out, int in, bool bias, int ld = 0) {
+        l.out = out;
+        l.in = in;
+        l.ld = ld ? ld : in;
+        K5_TRY(alloc(&l.W, static_cast<size_t>(out) * l.ld));
+        K5_CHECK_CUDA(cudaMemset(l.W, 0, static_cast<size_t>(out) * l.ld * sizeof(bf16)));
+        if (bias) K5_TRY(alloc(&l.b, out));
+        return K5_OK;
+    }
+    ~Engine() {
+        for (void* p : allocs) cudaFree(p);
+        if (stage) cudaFree(stage);
+    }
+};
+
+namespace {
+
+void expect_lin(Engine* e, const std::string& name, bool bias = true) {
+    e->expected.insert(name + ".weight");
+    if (bias) e->expected.insert(name + ".bias");
+}
+void expect_attn(Engine* e, const std::string& p) {
+    for (const char* n : {"to_query", "to_key", "to_value", "out_layer"}) expect_lin(e, p + n);
+    e->expected.insert(p + "query_norm.weight");
+    e->expected.insert(p + "key_norm.weight");
+}
+
+int alloc_attn(Engine* e, AttnW& a, bool cross) {
+    const int D = e->D;
+    if (!cross) {
+        K5_TRY(e->alloc_lin(a.qkv, 3 * D, D, true));
+    } else {
+        K5_TRY(e->alloc_lin(a.qkv, D, D, true));
+        K5_TRY(e->alloc_lin(a.kv, 2 * D, D, true));
+    }
+    K5_TRY(e->alloc_lin(a.o, D, D, true));
+    K5_TRY(e->alloc(&a.qn, 64));
+    K5_TRY(e->alloc(&a.kn, 64));
+    return K5_OK;
+}
+
+int engine_init(Engine* e) {
+    const k5_config& c = e->c;
+    K5_REQUIRE(c.patch_size[0] == 1 && c.patch_size[1] == 2 && c.patch_size[2] == 2, "only patch_size (1,2,2) is supported");
+    K5_REQUIRE(c.axes_dims[0] + c.axes_dims[1] + c.axes_dims[2] == 64, "head_dim (sum of axes_dims) must be 64");
+    K5_REQUIRE(c.model_dim % 256 == 0 && c.model_dim <= 2048, "model_dim must be a multiple of 256 and <= 2048");
+    K5_REQUIRE(c.ff_dim % 64 == 0 && c.time_dim % 128 == 0 && c.time_dim <= 1024, "ff_dim x64, time_dim x128 <= 1024");
+    K5_REQUIRE(c.in_text_dim % 8 == 0 && c.in_text_dim2 % 8 == 0, "text dims must be multiples of 8");
+    K5_REQUIRE(c.max_tokens > 0 && c.max_text_tokens > 0 && c.max_text_tokens <= 1024, "bad workspace bounds");
+    K5_REQUIRE(4 * c.out_visual_dim == 64, "out_visual_dim must be 16 (patch 1x2x2 -> 64 output features)");
+    e->D = c.model_dim;
+    e->F = c.ff_dim;
+    e->Td = c.time_dim;
+    e->heads = c.model_dim / 64;
+    e->Cin = c.visual_cond ? 2 * c.in_visual_dim + 1 : c.in_visual_dim;
+    e->KP = ((4 * e->Cin + 63) / 64) * 64;
+    const int D = e->D, F = e->F, Td = e->Td;
+    const size_t S = c.max_tokens, L = c.max_text_tokens;
+
+    e->mod_rows = static_cast<size_t>(c.num_text_blocks) * 6 * D + static_cast<size_t>(c.num_visual_blocks) * 9 * D + 2 * D;
+    K5_TRY(e->alloc(&e->modW, e->mod_rows * Td));
+    K5_TRY(e->alloc(&e->modB, e->mod_rows));
+    K5_TRY(e->alloc(&e->modOut, e->mod_rows));
+    K5_TRY(e->alloc(&e->time_in_W, static_cast<size_t>(Td) * D));
+    K5_TRY(e->alloc(&e->time_in_b, Td));
+    K5_TRY(e->alloc(&e->time_out_W, static_cast<size_t>(Td) * Td));
+    K5_TRY(e->alloc(&e->time_out_b, Td));
+    K5_TRY(e->alloc_lin(e->text_in, D, c.in_text_dim, true));
+    K5_TRY(e->alloc_lin(e->pooled_in, Td, c.in_text_dim2, true));
+    K5_TRY(e->alloc_lin(e->vis_in, D, 4 * e->Cin, true, e->KP));
+    K5_TRY(e->alloc_lin(e->out_lin, 4 * c.out_visual_dim, D, true));
+    K5_TRY(e->alloc(&e->text_ln_w, D));
+    K5_TRY(e->alloc(&e->text_ln_b, D));
+    K5_TRY(e->alloc(&e->pooled_ln_w, Td));
+    K5_TRY(e->alloc(&e->pooled_ln_b, Td));
+    K5_TRY(e->alloc(&e->freqs, D / 2));
+    K5_TRY(e->alloc(&e->args_text, 1024 * 32));
+    for (int i = 0; i < 3; ++i) K5_TRY(e->alloc(&e->args_ax[i], 128 * (c.axes_dims[i] / 2)));
+
+    expect_lin(e, "time_embeddings.in_layer");
+    expect_lin(e, "time_embeddings.out_layer");
+    expect_lin(e, "text_embeddings.in_layer");
+    e->expected.insert("text_embeddings.norm.weight");
+    e->expected.insert("text_embeddings.norm.bias");
+    expect_lin(e, "pooled_text_embeddings.in_layer");
+    e->expected.insert("pooled_text_embeddings.norm.weight");
+    e->expected.insert("pooled_text_embeddings.norm.bias");
+    expect_lin(e, "visual_embeddings.in_layer");
+    expect_lin(e, "out_layer.modulation.out_layer");
+    expect_lin(e, "out_layer.out_layer");
+    for (const char* n : {"time_embeddings.freqs", "text_rope_embeddings.args", "visual_rope_embeddings.args_0",
+                          "visual_rope_embeddings.args_1", "visual_rope_embeddings.args_2"})
+        e->expected.insert(n);
+
+    size_t off = 0;
+    e->tblocks.resize(c.num_text_blocks);
+    for (int i = 0; i < c.num_text_blocks; ++i) {
+        Block& b = e->tblocks[i];
+        b.mod_off = off;
+        off += 6 * D;
+        K5_TRY(alloc_attn(e, b.self, false));
+        K5_TRY(e->alloc_lin(b.ff_in, F, D, false));
+        K5_TRY(e->alloc_lin(b.ff_out, D, F, false));
+        const std::string p = "text_transformer_blocks." + std::to_string(i) + ".";
+        expect_lin(e, p + "text_modulation.out_layer");
+        expect_attn(e, p + "self_attention.");
+        expect_lin(e, p + "feed_forward.in_layer", false);
+        expect_lin(e, p + "feed_forward.out_layer", false);
+    }
+    e->vblocks.resize(c.num_visual_blocks);
+    for (int i = 0; i < c.num_visual_blocks; ++i) {
+        Block& b = e->vblocks[i];
+        b.mod_off = off;
+        off += 9 * D;
+        K5_TRY(alloc_attn(e, b.self, false));
+        K5_TRY(alloc_attn(e, b.cross, true));
+        K5_TRY(e->alloc_lin(b.ff_in, F, D, false));
+        K5_TRY(e->alloc_lin(b.ff_out, D, F, false));
+        const std::string p = "visual_transformer_blocks." + std::to_string(i) + ".";
+        expect_lin(e, p + "visual_modulation.out_layer");
+        expect_attn(e, p + "self_attention.");
+        expect_attn(e, p + "cross_attention.");
+        expect_lin(e, p + "feed_forward.in_layer", false);
+        expect_lin(e, p + "feed_forward.out_layer", false);
+    }
+    e->out_mod_off = off;
+
+    // workspace
+    K5_TRY(e->alloc(&e->x, S * D));
+    K5_TRY(e->alloc(&e->xn, S * D));
+    K5_TRY(e->alloc(&e->qkv, S * 3 * D));
+    K5_TRY(e->alloc(&e->att, S * D));
+    K5_TRY(e->alloc(&e->hid, S * F));
+    K5_TRY(e->alloc(&e->patchA, S * e->KP));
+    K5_TRY(e->alloc(&e->y64, S * 64));
+    K5_TRY(e->alloc(&e->te, L * D));
+    K5_TRY(e->alloc(&e->ten, L * D));
+    K5_TRY(e->alloc(&e->tqkv, L * 3 * D));
+    K5_TRY(e->alloc(&e->tatt, L * D));
+    K5_TRY(e->alloc(&e->thid, L * F));
+    K5_TRY(e->alloc(&e->tproj, L * D));
+    K5_TRY(e->alloc(&e->ckv, L * 2 * D));
+    K5_TRY(e->alloc(&e->tfeat, D));
+    K5_TRY(e->alloc(&e->t1, Td));
+    K5_TRY(e->alloc(&e->tembed, Td));
+    K5_TRY(e->alloc(&e->rope_v, S * 32));
+    K5_TRY(e->alloc(&e->rope_t, L * 32));
+    K5_TRY(e->alloc(&e->rope_t_arange, L * 32));
+    K5_TRY(e->alloc(&e->pos_dev, 8192));
+    K5_TRY(e->alloc(&e->v_c, S * 64));
+    K5_TRY(e->alloc(&e->v_u, S * 64));
+    K5_TRY(e->alloc(&e->density_acc, 2));
+    return K5_OK;
+}
+
+
+struct Dest {
+    enum Kind { NONE, BF16_MAT, F32_ROUND, F32 } kind = NONE;
+    void* ptr = nullptr;
+    int rows = 0, cols = 0, ld = 0;
+};
+
+// key -> destination inside the engine's repacked storage
+Dest resolve(Engine* e, const std::string& key) {
+    Dest d;
+    const int D = e->D, Td = e->Td;
+    auto mat = [&](Lin& l, int row0, int rows) {
+        d.kind = Dest::BF16_MAT;
+        d.ptr = l.W + static_cast<size_t>(row0) * l.ld;
+        d.rows = rows;
+        d.cols = l.in;
+        d.ld = l.ld;
+    };
+    auto vec_round = [&](float* p, int n) {
+        d.kind = Dest::F32_ROUND;
+        d.ptr = p;
+        d.rows = 1;
+        d.cols = n;
+    };
+    auto f32 = [&](float* p, int rows, int cols) {
+        d.kind = Dest::F32;
+        d.ptr = p;
+        d.rows = rows;
+        d.cols = cols;
+    };
+    auto lin = [&](Lin& l, const std::string& suffix, int row0 = 0, int rows = -1) {
+        if (rows < 0) rows = l.out;
+        if (suffix == "weight") mat(l, row0, rows);
+        else if (suffix == "bias" && l.b) vec_round(l.b + row0, rows);
+    };
+    auto attn = [&](AttnW& a, bool cross, const std::string& rest) {
+        const std::string suf = rest.substr(rest.rfind('.') + 1);
+        if (rest.rfind("to_query.", 0) == 0) lin(a.qkv, suf, 0, D);
+        else if (rest.rfind("to_key.", 0) == 0) cross ? lin(a.kv, suf, 0, D) : lin(a.qkv, suf, D, D);
+        else if (rest.rfind("to_value.", 0) == 0) cross ? lin(a.kv, suf, D, D) : lin(a.qkv, suf, 2 * D, D);
+        else if (rest.rfind("out_layer.", 0) == 0) lin(a.o, suf);
+        else if (rest == "query_norm.weight") f32(a.qn, 1, 64);
+        else if (rest == "key_norm.weight") f32(a.kn, 1, 64);
+    };
+    auto modl = [&](size_t off, int n, const std::string& suf) {
+        if (suf == "weight") f32(e->modW + off * Td, n, Td);
+        else if (suf == "bias") f32(e->modB + off, 1, n);
+    };
+    const std::string suf = key.substr(key.rfind('.') + 1);
+    if (key == "time_embeddings.freqs") f32(e->freqs, 1, D / 2);
+    else if (key == "text_rope_embeddings.args") f32(e->args_text, 1024, 32);
+    else if (key.rfind("visual_rope_embeddings.args_", 0) == 0) {
+        const int i = key.back() - '0';
+        if (i >= 0 && i < 3) f32(e->args_ax[i], 128, e->c.axes_dims[i] / 2);
+    } else if (key == "time_embeddings.in_layer.weight") f32(e->time_in_W, Td, D);
+    else if (key == "time_embeddings.in_layer.bias") f32(e->time_in_b, 1, Td);
+    else if (key == "time_embeddings.out_layer.weight") f32(e->time_out_W, Td, Td);
+    else if (key == "time_embeddings.out_layer.bias") f32(e->time_out_b, 1, Td);
+    else if (key.rfind("text_embeddings.in_layer.", 0) == 0) lin(e->text_in, suf);
+    else if (key == "text_embeddings.norm.weight") f32(e->text_ln_w, 1, D);
+    else if (key == "text_embeddings.norm.bias") f32(e->text_ln_b, 1, D);
+    else if (key.rfind("pooled_text_embeddings.in_layer.", 0) == 0) lin(e->pooled_in, suf);
+    else if (key == "pooled_text_embeddings.norm.weight") f32(e->pooled_ln_w, 1, Td);
+    else if (key == "pooled_text_embeddings.norm.bias") f32(e->pooled_ln_b, 1, Td);
+    else if (key.rfind("visual_embeddings.in_layer.", 0) == 0) lin(e->vis_in, suf);
+    else if (key.rfind("out_layer.modulation.out_layer.", 0) == 0) modl(e->out_mod_off, 2 * D, suf);
+    else if (key.rfind("out_layer.out_layer.", 0) == 0) lin(e->out_lin, suf);
+    else {
+        const bool text = key.rfind("text_transformer_blocks.", 0) == 0;
+        const bool vis = key.rfind("visual_transformer_blocks.", 0) == 0;
+        if (text || vis) {
+            const size_t p0 = key.find('.') + 1;
+            const size_t p1 = key.find('.', p0);
+            const int idx = atoi(key.substr(p0, p1 - p0).c_str());
+            std::vector<Block>& blocks = text ? e->tblocks : e->vblocks;
+            if (idx >= 0 && idx < static_cast<int>(blocks.size())) {
+                Block& b = blocks[idx];
+                const std::string rest = key.substr(p1 + 1);
+                if (rest.rfind("text_modulation.out_layer.", 0) == 0 && text) modl(b.mod_off, 6 * D, suf);
+                else if (rest.rfind("visual_modulation.out_layer.", 0) == 0 && vis) modl(b.mod_off, 9 * D, suf);
+                else if (rest.rfind("self_attention.", 0) == 0) attn(b.self, false, rest.substr(15));
+                else if (rest.rfind("cross_attention.", 0) == 0 && vis) attn(b.cross, true, rest.substr(16));
+                else if (rest == "feed_forward.in_layer.weight") mat(b.ff_in, 0, b.ff_in.out);
+                else if (rest == "feed_forward.out_layer.weight") mat(b.ff_out, 0, b.ff_out.out);
+            }
+        }
+    }
+    return d;
+}
+
+int dtype_size(int dt) { return dt == 0 ? 4 : 2; }
+
+}  // namespace
+
+int engine_load_tensor(Engine* e, const char* key_c, const void* data, int dtype, const int64_t* shape, int ndim) {
+    K5_REQUIRE(key_c && data && shape, "load_tensor: null argument");
+    K5_REQUIRE(dtype >= 0 && dtype <= 2, "load_tensor: dtype must be 0 (f32), 1 (bf16) or 2 (f16)");
+    const std::string key(key_c);
+    if (!e->expected.count(key)) {
+        set_last_error("load_tensor: unexpected key '" + key + "'");
+        return K5_ERR_INVALID;
+    }
+    Dest d = resolve(e, key);
+    if (d.kind == Dest::NONE) {
+        set_last_error("load_tensor: no destination for key '" + key + "'");
+        return K5_ERR_INVALID;
+    }
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= static_cast<size_t>(shape[i]);
+    const size_t want = static_cast<size_t>(d.rows) * d.cols;
+    bool shape_ok = (n == want);
+    if (shape_ok && ndim == 2) shape_ok = (shape[0] == d.rows && shape[1] == d.cols);
+    if (!shape_ok) {
+        set_last_error("load_tensor: shape mismatch for '" + key + "': expected [" + std::to_string(d.rows) + ", " +
+                       std::to_string(d.cols) + "], got " + std::to_string(n) + " elements");
+        return K5_ERR_INVALID;
+    }
+    const size_t bytes = n * dtype_size(dtype);
+    if (bytes > e->stage_bytes) {
+        if (e->stage) cudaFree(e->stage);
+        e->stage = nullptr;
+        e->stage_bytes = 0;
+        K5_CHECK_CUDA(cudaMalloc(&e->stage, bytes));
+        e->stage_bytes = bytes;
+    }
+    K5_CHECK_CUDA(cudaMemcpy(e->stage, data, bytes, cudaMemcpyDefault));
+    if (d.kind == Dest::BF16_MAT) K5_TRY(convert_to_bf16(e->stage, dtype, static_cast<bf16*>(d.ptr), d.rows, d.cols, d.ld, 0));
+    else K5_TRY(convert_to_f32(e->stage, dtype, static_cast<float*>(d.ptr), n, d.kind == Dest::F32_ROUND, 0));
+    K5_CHECK_CUDA(cudaStreamSynchronize(0));
+    e->loaded.insert(key);
+    return K5_OK;
+}
+
+int engine_finalize(Engine* e) {
+    std::string missing;
+    int n = 0;
+    for (const std::string& k : e->expected)
+        if (!e->loaded.count(k)) {
+            if (n++ < 8) missing += (missing.empty() ? "" : ", ") + k;
+        }
+    if (n) {
+        set_last_error("finalize: " + std::to_string(n) + " tensors missing: " + missing + (n > 8 ? ", ..." : ""));
+        return K5_ERR_STATE;
+    }
+    if (e->stage) {
+        cudaFree(e->stage);
+        e->stage = nullptr;
+        e->stage_bytes = 0;
+    }
+    {
+        const int L = e->c.max_text_tokens;
+        std::vector<int> pos(L);
+        for (int i = 0; i < L; ++i) pos[i] = i;
+        K5_CHECK_CUDA(cudaMemcpy(e->pos_dev + 4096, pos.data(), L * sizeof(int), cudaMemcpyHostToDevice));
+        K5_TRY(rope1d_table(e->args_text, 32, e->pos_dev + 4096, L, e->rope_t_arange, 0));
+        K5_CHECK_CUDA(cudaStreamSynchronize(0));
+    }
+    e->finalized = true;
+    return K5_OK;
+}
+
+int engine_set_grid(Engine* e, int T, int H, int W, const int32_t* pt, const int32_t* ph, const int32_t* pw,
+                    const float sf[3], int fractal) {
+    K5_REQUIRE(e->finalized, "set_grid: call k5_engine_finalize first (the RoPE buffers come with the weights)");
+    K5_REQUIRE(T > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "set_grid: latent H, W must be even and positive");
+    const int Hp = H / 2, Wp = W / 2;
+    const size_t S = static_cast<size_t>(T) * Hp * Wp;
+    K5_REQUIRE(S <= static_cast<size_t>(e->c.max_tokens), "set_grid: token count exceeds max_tokens of the engine");
+    K5_REQUIRE(T <= 128 && Hp <= 128 && Wp <= 128, "set_grid: RoPE tables hold 128 positions per axis");
+    K5_REQUIRE(!fractal || (Hp % 8 == 0 && Wp % 8 == 0), "set_grid: fractal order needs H/2, W/2 divisible by 8");
+    K5_REQUIRE(sf && sf[0] != 0.f && sf[1] != 0.f && sf[2] != 0.f, "set_grid: scale_factor must be non-zero");
+    std::vector<int> pos(T + Hp + Wp);
+    for (int i = 0; i < T; ++i) pos[i] = pt ? pt[i] : i;
+    for (int i = 0; i < Hp; ++i) pos[T + i] = ph ? ph[i] : i;
+    for (int i = 0; i < Wp; ++i) pos[T + Hp + i] = pw ? pw[i] : i;
+    for (int v : pos) K5_REQUIRE(v >= 0 && v < 128, "set_grid: RoPE position out of range [0,128)");
+    K5_CHECK_CUDA(cudaMemcpy(e->pos_dev, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const k5_config& c = e->c;
+    K5_TRY(rope3d_table(e->args_ax[0], e->args_ax[1], e->args_ax[2], c.axes_dims[0] / 2, c.axes_dims[1] / 2,
+                        c.axes_dims[2] / 2, e->pos_dev, e->pos_dev + T, e->pos_dev + T + Hp, sf, T, Hp, Wp, fractal != 0,
+                        e->rope_v, 0));
+    K5_CHECK_CUDA(cudaStreamSynchronize(0));
+    e->T = T;
+    e->Hp = Hp;
+    e->Wp = Wp;
+    e->S = static_cast<int>(S);
+    e->fractal = fractal ? 1 : 0;
+    e->grid_set = true;
+    return K5_OK;
+}
+
+namespace {
+
+int lin_gemm(const bf16* A, int lda, const Lin& l, int M, int epi, GemmEpilogue& ep, cudaStream_t st) {
+    ep.bias = l.b;
+    count_launch(1);
+    return gemm_bf16(A, lda, l.W, l.ld, M, l.out, l.ld, epi, ep, st);
+}
+
+int ensure_nabla(Engine* e, const k5_sparse* sp) {
+    const int nb = e->S / 64;
+    const int Tb = e->T, Hb = e->Hp / 8, Wb = e->Wp / 8;
+    if (!e->kv_count) {
+        const size_t nbmax = e->c.max_tokens / 64;
+        K5_TRY(e->alloc(&e->kv_count, static_cast<size_t>(e->heads) * nbmax));
+        K5_TRY(e->alloc(&e->kv_index, static_cast<size_t>(e->heads) * nbmax * nbmax));
+        K5_TRY(e->alloc(&e->nabla_ws, nabla_workspace_floats(static_cast<int>(nbmax) * 64, e->heads)));
+        K5_TRY(e->alloc(&e->sta, nbmax * nbmax));
+    }
+    const int key[6] = {Tb, Hb, Wb, sp->wT, sp->wH, sp->wW};
+    bool same = true;
+    for (int i = 0; i < 6; ++i) same = same && key[i] == e->sta_key[i];
+    if (!same) {
+        K5_REQUIRE(Tb * Hb * Wb == nb, "NABLA: block grid does not match the token count");
+        count_launch(1);
+        K5_TRY(sta_mask(Tb, Hb, Wb, sp->wT, sp->wH, sp->wW, e->sta, 0));
+        K5_CHECK_CUDA(cudaStreamSynchronize(0));
+        for (int i = 0; i < 6; ++i) e->sta_key[i] = key[i];
+    }
+    return K5_OK;
+}
+
+// One attention sub-layer output projection + gated residual: x = bf16(x + gate * (att . Wo^T + b))
+int out_proj_gate(Engine* e, const bf16* att, const Lin& o, bf16* x, const float* gate, int M, cudaStream_t st) {
+    GemmEpilogue ep;
+    ep.out = x;
+    ep.ldo = e->D;
+    ep.resid = x;
+    ep.ldr = e->D;
+    ep.gate = gate;
+    return lin_gemm(att, e->D, o, M, EPI_GATE, ep, st);
+}
+
+int feed_forward(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* hid, const float* mod, int M, cudaStream_t st) {
+    const int D = e->D, F = e->F;
+    count_launch(1);
+    K5_TRY(ln_rows(x, D, xn, D, M, D, mod + D, mod, true, LN_EPS, st));
+    GemmEpilogue g1;
+    g1.out = hid;
+    g1.ldo = F;
+    K5_TRY(lin_gemm(xn, D, b.ff_in, M, EPI_GELU, g1, st));
+    GemmEpilogue g2;
+    g2.out = x;
+    g2.ldo = D;
+    g2.resid = x;
+    g2.ldr = D;
+    g2.gate = mod + 2 * D;
+    return lin_gemm(hid, F, b.ff_out, M, EPI_GATE, g2, st);
+}
+
+int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16* att, const float* mod, int M,
+                   const float2* rope, const k5_sparse* sp, cudaStream_t st) {
+    const int D = e->D;
+    count_launch(1);
+    K5_TRY(ln_rows(x, D, xn, D, M, D, mod + D, mod, true, LN_EPS, st));
+    GemmEpilogue g;
+    g.out = qkv;
+    g.ldo = 3 * D;
+    g.norm_w0 = b.self.qn;
+    g.norm_w1 = b.self.kn;
+    g.norm_split = D;
+    g.norm_cols = 2 * D;
+    g.rope_cols = 2 * D;
+    g.rope = rope;
+    K5_TRY(lin_gemm(xn, D, b.self.qkv, M, EPI_HEADS, g, st));
+    const int32_t *cnt = nullptr, *idx = nullptr;
+    if (sp) {
+        count_launch(nabla_select_launches());
+        K5_TRY(nabla_select(qkv, 3 * D, qkv + D, 3 * D, M, e->heads, sp->P, sp->add_sta ? e->sta : nullptr, e->kv_count,
+                            e->kv_index, e->nabla_ws, e->density_acc, st));
+        cnt = e->kv_count;
+        idx = e->kv_index;
+    }
+    count_launch(1);
+    K5_TRY(attention_fwd(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, att, D, M, M, e->heads, 0.125f, cnt, idx, st));
+    return out_proj_gate(e, att, b.self.o, x, mod + 2 * D, M, st);
+}
+
+int cross_attention(Engine* e, const Block& b, const bf16* text, int L, const float* mod, cudaStream_t st) {
+    const int D = e->D, M = e->S;
+    count_launch(1);
+    K5_TRY(ln_rows(e->x, D, e->xn, D, M, D, mod + D, mod, true, LN_EPS, st));
+    GemmEpilogue gq;                 // q = RMSNorm(to_query(x)); no RoPE (nn.py:343-349)
+    gq.out = e->qkv;
+    gq.ldo = D;
+    gq.norm_w0 = b.cross.qn;
+    gq.norm_w1 = b.cross.qn;
+    gq.norm_split = D;
+    gq.norm_cols = D;
+    K5_TRY(lin_gemm(e->xn, D, b.cross.qkv, M, EPI_HEADS, gq, st));
+    GemmEpilogue gk;                 // [k | v] = text . [Wk | Wv]^T, k normed
+    gk.out = e->ckv;
+    gk.ldo = 2 * D;
+    gk.norm_w0 = b.cross.kn;
+    gk.norm_w1 = b.cross.kn;
+    gk.norm_split = D;
+    gk.norm_cols = D;
+    K5_TRY(lin_gemm(text, D, b.cross.kv, L, EPI_HEADS, gk, st));
+    count_launch(1);
+    K5_TRY(attention_fwd(e->qkv, D, e->ckv, 2 * D, e->ckv + D, 2 * D, e->att, D, M, L, e->heads, 0.125f, nullptr, nullptr, st));
+    return out_proj_gate(e, e->att, b.cross.o, e->x, mod + 2 * D, M, st);
+}
+
+}  // namespace
+
+int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, const int32_t* text_pos, const bf16* pooled,
+                   float time, const k5_sparse* sp, bf16* out, cudaStream_t st) {
+    K5_REQUIRE(e->finalized, "forward: call k5_engine_finalize first");
+    K5_REQUIRE(e->grid_set, "forward: call k5_engine_set_grid first");
+    K5_REQUIRE(x && text && pooled && out, "forward: null tensor");
+    K5_REQUIRE(Cx == e->Cin || Cx == e->c.in_visual_dim, "forward: x must have model-input or latent channel count");
+    K5_REQUIRE(L > 0 && L <= e->c.max_text_tokens, "forward: text length out of range");
+    K5_REQUIRE(!sp || e->fractal, "forward: NABLA needs the fractal token order (set_grid fractal=1)");
+    K5_REQUIRE(!sp || e->S % 64 == 0, "forward: NABLA needs a token count divisible by 64");
+    const int D = e->D, Td = e->Td, S = e->S;
+    if (sp) K5_TRY(ensure_nabla(e, sp));
+    e->last_sparse = sp != nullptr;
+    e->last_stream = st;
+    if (sp) K5_CHECK_CUDA(cudaMemsetAsync(e->density_acc, 0, 2 * sizeof(float), st));
+
+    // --- before_text_transformer_blocks (dit.py:130-137)
+    count_launch(5);
+    K5_TRY(time_features(e->freqs, time, e->tfeat, D / 2, st));
+    K5_TRY(gemv_f32(e->time_in_W, e->time_in_b, e->tfeat, e->t1, Td, D, false, true, st));
+    K5_TRY(gemv_f32(e->time_out_W, e->time_out_b, e->t1, e->tembed, Td, Td, false, false, st));
+    K5_TRY(pooled_embed(e->pooled_in.W, e->pooled_in.b, e->pooled_ln_w, e->pooled_ln_b, pooled, e->c.in_text_dim2, Td,
+                        e->tembed, LN_EPS, st));
+    // every Modulation layer of the forward in one GEMV (nn.py:161-164): Linear(SiLU(time_embed))
+    K5_TRY(gemv_f32(e->modW, e->modB, e->tembed, e->modOut, static_cast<int>(e->mod_rows), Td, true, false, st));
+
+    {   // text_embeddings (nn.py:70-72)
+        GemmEpilogue g;
+        g.out = e->tproj;
+        g.ldo = D;
+        K5_TRY(lin_gemm(text, e->c.in_text_dim, e->text_in, L, EPI_STORE, g, st));
+        count_launch(1);
+        K5_TRY(ln_rows(e->tproj, D, e->te, D, L, D, e->text_ln_w, e->text_ln_b, false, LN_EPS, st));
+    }
+    {   // visual_embeddings (nn.py:81-96), rows written directly in engine token order
+        count_launch(1);
+        K5_TRY(patchify(x, Cx, e->Cin, e->T, e->Hp, e->Wp, e->fractal != 0, e->patchA, e->KP, st));
+        GemmEpilogue g;
+        g.out = e->x;
+        g.ldo = D;
+        K5_TRY(lin_gemm(e->patchA, e->KP, e->vis_in, S, EPI_STORE, g, st));
+    }
+    // text RoPE (nn.py:110-116): arange positions use the table built at finalize (a prefix of it)
+    const float2* rope_t = e->rope_t_arange;
+    if (text_pos) {
+        std::vector<int> pos(text_pos, text_pos + L);
+        for (int v : pos) K5_REQUIRE(v >= 0 && v < 1024, "forward: text RoPE position out of range [0,1024)");
+        K5_CHECK_CUDA(cudaMemcpyAsync(e->pos_dev + 4096, pos.data(), L * sizeof(int), cudaMemcpyHostToDevice, st));
+        K5_CHECK_CUDA(cudaStreamSynchronize(st));   // pos is a local staging buffer
+        count_launch(1);
+        K5_TRY(rope1d_table(e->args_text, 32, e->pos_dev + 4096, L, e->rope_t, st));
+        rope_t = e->rope_t;
+    }
+    // --- text transformer blocks (dit.py:33-44)
+    for (const Block& b : e->tblocks) {
+        const float* mod = e->modOut + b.mod_off;
+        K5_TRY(self_attention(e, b, e->te, e->ten, e->tqkv, e->tatt, mod, L, rope_t, nullptr, st));
+        K5_TRY(feed_forward(e, b, e->te, e->ten, e->thid, mod + 3 * D, L, st));
+    }
+    // --- visual transformer blocks (dit.py:61-79)
+    for (const Block& b : e->vblocks) {
+        const float* mod = e->modOut + b.mod_off;
+        K5_TRY(self_attention(e, b, e->x, e->xn, e->qkv, e->att, mod, S, e->rope_v, sp, st));
+        K5_TRY(cross_attention(e, b, e->te, L, mod + 3 * D, st));
+        K5_TRY(feed_forward(e, b, e->x, e->xn, e->hid, mod + 6 * D, S, st));
+    }
+    // --- after_blocks / OutLayer (dit.py:150-153, nn.py:374-400)
+    {
+        const float* mod = e->modOut + e->out_mod_off;     // (shift, scale)
+        count_launch(2);
+        K5_TRY(ln_rows(e->x, D, e->xn, D, S, D, mod + D, mod, true, LN_EPS, st));
+        GemmEpilogue g;
+        g.out = e->y64;
+        g.ldo = 64;
+        K5_TRY(lin_gemm(e->xn, D, e->out_lin, S, EPI_STORE, g, st));
+        K5_TRY(unpatchify(e->y64, 64, e->T, e->Hp, e->Wp, e->fractal != 0, e->c.out_visual_dim, out, st));
+    }
+    return K5_OK;
+}
+
+int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, const bf16* text, int L, const bf16* pooled,
+                  const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st) {
+    K5_REQUIRE(e->grid_set, "sample: call k5_engine_set_grid first");
+    K5_REQUIRE(num_steps > 0 && img, "sample: bad arguments");
+    const bool cfg = fabsf(w - 1.0f) > 1e-6f;
+    K5_REQUIRE(!cfg || (ntext && npooled && Ln > 0), "sample: guidance needs the null-text embeddings");
+    const size_t n = static_cast<size_t>(e->S) * 64;   // T*H*W*16 latent elements
+    // timesteps (generation_utils.py:102-103): linspace(1, 0, N+1), t <- s t / (1 + (s - 1) t), all fp32 like torch
+    std::vector<float> ts(num_steps + 1);
+    for (int i = 0; i <= num_steps; ++i) {
+        // torch.linspace: start + step * i for the first half, end - step * (N - i) for the second
+        const float step = (0.0f - 1.0f) / static_cast<float>(num_steps);
+        const float t = (i < (num_steps + 1) / 2) ? 1.0f + step * static_cast<float>(i)
+                                                  : 0.0f - step * static_cast<float>(num_steps - i);
+        ts[i] = (sched * t) / (1.0f + (sched - 1.0f) * t);
+    }
+    for (int i = 0; i < num_steps; ++i) {
+        const float t = ts[i], dt = ts[i + 1] - ts[i];
+        K5_TRY(engine_forward(e, img, e->c.in_visual_dim, text, L, nullptr, pooled, t * 1000.0f, sp, e->v_c, st));
+        const bf16* v = e->v_c;
+        if (cfg) {
+            K5_TRY(engine_forward(e, img, e->c.in_visual_dim, ntext, Ln, nullptr, npooled, t * 1000.0f, sp, e->v_u, st));
+            count_launch(1);
+            K5_TRY(cfg_combine(e->v_c, e->v_u, w, e->v_c, n, st));
+        }
+        count_launch(1);
+        K5_TRY(euler_step(img, v, dt, n, st));
+    }
+    return K5_OK;
+}
+
+float engine_density(Engine* e) {
+    if (!e->last_sparse) return 1.0f;
+    float h[2] = {0.f, 0.f};
+    cudaStreamSynchronize(e->last_stream);
+    cudaMemcpy(h, e->density_acc, sizeof(h), cudaMemcpyDeviceToHost);
+    return h[1] > 0.f ? h[0] / h[1] : 1.0f;
+}
+
+Engine* engine_new(const k5_config* cfg, int* rc) {
+    Engine* e = new Engine();
+    e->c = *cfg;
+    *rc = engine_init(e);
+    if (*rc != K5_OK) {
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+void engine_delete(Engine* e) { delete e; }
+
+}  // namespace k5

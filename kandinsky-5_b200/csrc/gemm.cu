@@ -1,0 +1,311 @@
+// bf16 GEMM on the 5th-gen tensor cores:  C[M,N] = A[M,K] . W[N,K]^T  (+ fused epilogue).
+//
+// This one kernel replaces every nn.Linear on the DiT hot path of the reference
+// (kandinsky/models/nn.py:181-184,206,235-237,284,317-319,341,354-361,376-382; SURVEY.md K4-K6,K13):
+//   * operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared
+//     memory ring, one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1),
+//   * the fp32 accumulator lives in TMEM, double-buffered (2 x BN columns) so that the epilogue of
+//     tile i overlaps the main loop of tile i+1,
+//   * the kernel is persistent (one CTA per SM, static tile schedule, N fastest so that the A rows
+//     of a wave are shared through L2 and W stays L2 resident),
+//   * the epilogue warps read TMEM with tcgen05.ld (thread = one output row) and apply the op that
+//     follows the Linear in the reference, so that no extra HBM round trip is needed:
+//       EPI_STORE : bf16(acc + bias)
+//       EPI_GELU  : bf16(gelu_erf(bf16(acc)))                               nn.py:356
+//       EPI_GATE  : bf16(x + gate * bf16(acc + bias))                       nn.py:30-33 (apply_gate_sum)
+//       EPI_HEADS : bf16(acc + bias) -> per-head RMSNorm (fp32) -> bf16 -> RoPE (fp32) -> bf16
+//                                                                           nn.py:246-250, 35-40
+// Rounding points follow SURVEY.md Appendix A.
+#include "common.h"
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace k5 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 GemmEpilogue e) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int n_tiles_n = N / BN;
+    const int n_tiles_m = (M + BM - 1) / BM;
+    const int num_tiles = n_tiles_m * n_tiles_n;
+    const int nkb = (K + BK - 1) / BK;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles_n) * BM;
+                const int n0 = (tile % n_tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = umma_desc_sw128(sa + k * 32, 0, 1024);
+                        const uint64_t bd = umma_desc_sw128(sb + k * 32, 0, 1024);
+                        umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);     // smem slot reusable once these MMAs have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[acc]);           // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (4 warps, thread = output row) =====================
+        const int wq = warp & 3;
+        const int lane = threadIdx.x & 31;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile / n_tiles_n) * BM;
+            const int n0 = (tile % n_tiles_n) * BN;
+            const int row = m0 + wq * 32 + lane;
+            const bool row_ok = row < M;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(wq * 32) << 16);
+
+            if constexpr (EPI == EPI_HEADS) {
+                // one head (64 columns) at a time
+                for (int c = 0; c < BN / 64; ++c) {
+                    uint32_t raw[64];
+                    tmem_ld32(t_row + c * 64, raw);
+                    tmem_ld32(t_row + c * 64 + 32, raw + 32);
+                    tmem_wait_ld();
+                    const int col0 = n0 + c * 64;
+                    float x[64];
+                    float ss = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        float b = e.bias ? __ldg(e.bias + col0 + i) : 0.f;
+                        x[i] = bf16_round(__uint_as_float(raw[i]) + b);
+                        ss += x[i] * x[i];
+                    }
+                    if (col0 < e.norm_cols) {
+                        const float* w = (col0 < e.norm_split) ? e.norm_w0 : e.norm_w1;
+                        const float inv = rsqrtf(ss * (1.0f / 64.0f) + 1.1920928955078125e-07f);
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) x[i] = bf16_round(x[i] * inv * __ldg(w + i));
+                        if (col0 < e.rope_cols && row_ok) {
+                            const float2* rp = e.rope + static_cast<size_t>(row) * 32;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float2 cs = __ldg(rp + i);
+                                const float a = x[2 * i], b2 = x[2 * i + 1];
+                                // reference: (rope * x_).sum(-1): products rounded separately, then added
+                                x[2 * i] = bf16_round(__fadd_rn(__fmul_rn(cs.x, a), __fmul_rn(-cs.y, b2)));
+                                x[2 * i + 1] = bf16_round(__fadd_rn(__fmul_rn(cs.y, a), __fmul_rn(cs.x, b2)));
+                            }
+                        }
+                    }
+                    if (row_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(e.out + static_cast<size_t>(row) * e.ldo + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            uint4 v;
+                            v.x = pack_bf16x2(x[8 * i + 0], x[8 * i + 1]);
+                            v.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
+                            v.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]);
+                            v.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
+                            dst[i] = v;
+                        }
+                    }
+                }
+            } else {
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t raw[32];
+                    tmem_ld32(t_row + c * 32, raw);
+                    tmem_wait_ld();
+                    const int col0 = n0 + c * 32;
+                    if (row_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(e.out + static_cast<size_t>(row) * e.ldo + col0);
+                        const uint4* res = nullptr;
+                        if constexpr (EPI == EPI_GATE)
+                            res = reinterpret_cast<const uint4*>(e.resid + static_cast<size_t>(row) * e.ldr + col0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float y[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int cc = 8 * i + j;
+                                float v = __uint_as_float(raw[cc]);
+                                if (e.bias) v += __ldg(e.bias + col0 + cc);
+                                y[j] = v;
+                            }
+                            if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) y[j] = gelu_erf(bf16_round(y[j]));
+                            }
+                            if constexpr (EPI == EPI_GATE) {
+                                const uint4 r = res[i];
+                                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float g0 = __ldg(e.gate + col0 + 8 * i + 2 * j);
+                                    const float g1 = __ldg(e.gate + col0 + 8 * i + 2 * j + 1);
+                                    y[2 * j] = __fadd_rn(bf16_lo(rr[j]), __fmul_rn(g0, bf16_round(y[2 * j])));
+                                    y[2 * j + 1] = __fadd_rn(bf16_hi(rr[j]), __fmul_rn(g1, bf16_round(y[2 * j + 1])));
+                                }
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(y[0], y[1]);
+                            o.y = pack_bf16x2(y[2], y[3]);
+                            o.z = pack_bf16x2(y[4], y[5]);
+                            o.w = pack_bf16x2(y[6], y[7]);
+                            dst[i] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN, int EPI>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool configured = false;
+    auto kern = gemm_bf16_kernel<BN, EPI>;
+    if (!configured) {
+        K5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * (N / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, e);
+    K5_CHECK_CUDA(cudaGetLastError());
+    return K5_OK;
+}
+
+template <int BN>
+int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& e,
+               cudaStream_t st) {
+    switch (epi) {
+        case EPI_STORE: return launch<BN, EPI_STORE>(tmA, tmB, M, N, K, e, st);
+        case EPI_GELU: return launch<BN, EPI_GELU>(tmA, tmB, M, N, K, e, st);
+        case EPI_GATE: return launch<BN, EPI_GATE>(tmA, tmB, M, N, K, e, st);
+        case EPI_HEADS: return launch<BN, EPI_HEADS>(tmA, tmB, M, N, K, e, st);
+    }
+    set_last_error("unknown GEMM epilogue");
+    return K5_ERR_INVALID;
+}
+
+}  // namespace
+
+int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int epi, const GemmEpilogue& e,
+              cudaStream_t st) {
+    K5_REQUIRE(M > 0 && N > 0 && K > 0, "GEMM: empty problem");
+    K5_REQUIRE(N % 64 == 0, "GEMM: N must be a multiple of 64");
+    K5_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "GEMM: K / pitches must be multiples of 8 elements");
+    K5_REQUIRE(e.out != nullptr && e.ldo % 8 == 0, "GEMM: output pitch must be a multiple of 8 elements");
+    if (epi == EPI_GATE) K5_REQUIRE(e.resid && e.gate && e.ldr % 8 == 0, "GEMM: gate epilogue needs resid/gate");
+    if (epi == EPI_HEADS) {
+        K5_REQUIRE(e.norm_cols % 64 == 0 && e.norm_split % 64 == 0 && e.rope_cols % 64 == 0, "GEMM: head split must be x64");
+        K5_REQUIRE(e.norm_cols == 0 || (e.norm_w0 && e.norm_w1), "GEMM: head epilogue needs norm weights");
+        K5_REQUIRE(e.rope_cols == 0 || e.rope, "GEMM: head epilogue needs a rope table");
+    }
+    const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+    CUtensorMap tmA, tmB;
+    K5_TRY(make_tmap_2d_bf16(&tmA, A, M, K, lda, BM));
+    K5_TRY(make_tmap_2d_bf16(&tmB, W, N, K, ldw, BN));
+    if (BN == 256) return launch_epi<256>(epi, tmA, tmB, M, N, K, e, st);
+    if (BN == 128) return launch_epi<128>(epi, tmA, tmB, M, N, K, e, st);
+    return launch_epi<64>(epi, tmA, tmB, M, N, K, e, st);
+}
+
+}  // namespace k5

@@ -1,0 +1,30 @@
+#pragma once
+#include "common.h"
+
+namespace k5 {
+
+enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GATE = 2, EPI_HEADS = 3 };
+
+struct GemmEpilogue {
+    bf16* out = nullptr;            // [M, N] row-major, pitch ldo
+    int ldo = 0;
+    const float* bias = nullptr;    // [N] (bf16-representable values held in fp32) or null
+    // EPI_GATE: out = bf16(resid + gate * bf16(acc + bias)); out may alias resid
+    const bf16* resid = nullptr;
+    int ldr = 0;
+    const float* gate = nullptr;    // [N] fp32
+    // EPI_HEADS (head_dim 64): columns [0, norm_cols) get per-head RMSNorm with weight norm_w0 for
+    // columns < norm_split and norm_w1 otherwise; columns [0, rope_cols) then get RoPE.
+    const float* norm_w0 = nullptr;
+    const float* norm_w1 = nullptr;
+    int norm_split = 0;
+    int norm_cols = 0;
+    int rope_cols = 0;
+    const float2* rope = nullptr;   // [M, 32] (cos, sin) per row and rotation pair
+};
+
+// C[M,N] = A[M,K] . W[N,K]^T with a fused epilogue; A, W bf16 row-major (K contiguous).
+int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, int epi, const GemmEpilogue& e,
+              cudaStream_t st);
+
+}  // namespace k5

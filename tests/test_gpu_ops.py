@@ -1,0 +1,162 @@
+"""Operator-level parity on a real B200: every kernel behind the C ABI against a plain torch fp32 restatement of
+the reference op it replaces (floating-point kernels -> torch fp32 reference with the reference's rounding points).
+Tolerances are stated per test; bf16 outputs are compared in units of bf16 ulps where that is meaningful."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from kandinsky import ops
+
+    return ops
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def bf16_ulp_err(a, b):
+    """max |a-b| in units of the bf16 spacing at |b| (2^-8 relative)."""
+    a, b = a.float(), b.float()
+    ulp = torch.maximum(b.abs(), torch.full_like(b, 1e-3)) * 2.0 ** -8
+    return float(((a - b).abs() / ulp).max())
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 256, 192), (1024, 1792, 1792), (37, 1792, 3584),
+                                   (1000, 64, 1792), (257, 128, 512), (4096, 7168, 1792), (2048, 1792, 7168)])
+def test_gemm_store_bias(M, N, K):
+    a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
+    bias = _rand((N,), 3).float()
+    out = _ops().linear(a, w, bias)
+    ref = (a.float() @ w.float().t() + bias).to(torch.bfloat16)
+    # fp32 accumulation order differs from torch's: allow 1 bf16 ulp on isolated elements
+    assert rel_l2(out, ref) < 2e-3
+    assert bf16_ulp_err(out, ref) <= 2.5
+    out2 = _ops().linear(a, w, None)
+    assert rel_l2(out2, (a.float() @ w.float().t()).to(torch.bfloat16)) < 2e-3
+
+
+def test_gemm_gelu():
+    M, N, K = 640, 1024, 256
+    a, w = _rand((M, K), 4), _rand((N, K), 5, K ** -0.5)
+    out = _ops().linear(a, w, None, epilogue="gelu")
+    h = (a.float() @ w.float().t()).to(torch.bfloat16)
+    ref = torch.nn.functional.gelu(h.float()).to(torch.bfloat16)         # nn.py:356, exact erf
+    assert rel_l2(out, ref) < 3e-3
+
+
+def test_gemm_gate_residual_in_place():
+    M, N, K = 517, 1792, 1792
+    a, w = _rand((M, K), 6), _rand((N, K), 7, K ** -0.5)
+    bias, gate = _rand((N,), 8).float(), _rand((N,), 9, dtype=torch.float32)
+    x = _rand((M, N), 10)
+    x0 = x.clone()
+    out = _ops().linear(a, w, bias, epilogue="gate", resid=x, gate=gate, out=x)   # out aliases resid
+    lin = (a.float() @ w.float().t() + bias).to(torch.bfloat16)
+    ref = (x0.float() + gate * lin.float()).to(torch.bfloat16)                  # nn.py:30-33
+    assert out.data_ptr() == x.data_ptr()
+    assert rel_l2(out, ref) < 3e-3
+
+
+def _heads_ref(a, w, bias, wq, wk, split, norm_cols, rope_cols, rope):
+    y = (a.float() @ w.float().t() + bias).to(torch.bfloat16)
+    M, N = y.shape
+    yh = y.float().view(M, N // 64, 64)
+    out = yh.clone()
+    nh = norm_cols // 64
+    if nh:
+        wsel = torch.stack([wq if h * 64 < split else wk for h in range(nh)])          # [nh,64]
+        n = yh[:, :nh]
+        n = n * torch.rsqrt(n.pow(2).mean(-1, keepdim=True) + torch.finfo(torch.float32).eps) * wsel
+        n = n.to(torch.bfloat16).float()                                               # nn.py:248-249
+        rh = rope_cols // 64
+        if rh:
+            c, s = rope[..., 0][:, None, :], rope[..., 1][:, None, :]                  # [M,1,32]
+            x0, x1 = n[:, :rh, 0::2], n[:, :rh, 1::2]
+            r = torch.stack([c * x0 + (-s) * x1, s * x0 + c * x1], dim=-1).flatten(-2)   # nn.py:35-40
+            n = torch.cat([r.to(torch.bfloat16).float(), n[:, rh:]], dim=1)
+        out[:, :nh] = n
+    return out.view(M, N).to(torch.bfloat16)
+
+
+def test_gemm_heads_qkv_norm_rope():
+    M, D = 333, 512
+    a, w = _rand((M, D), 11), _rand((3 * D, D), 12, D ** -0.5)
+    bias = _rand((3 * D,), 13).float()
+    wq, wk = 1 + 0.1 * _rand((64,), 14, dtype=torch.float32), 1 + 0.1 * _rand((64,), 15, dtype=torch.float32)
+    ang = _rand((M, 32), 16, 3.0, torch.float32)
+    rope = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+    out = _ops().linear(a, w, bias, epilogue="heads", norm_w0=wq, norm_w1=wk, norm_split=D, norm_cols=2 * D,
+                        rope_cols=2 * D, rope=rope)
+    ref = _heads_ref(a, w, bias, wq, wk, D, 2 * D, 2 * D, rope)
+    assert rel_l2(out, ref) < 4e-3
+    # cross-attention flavour: k normed, v plain, no rope (nn.py:343-349)
+    out2 = _ops().linear(a, w[: 2 * D], bias[: 2 * D].contiguous(), epilogue="heads", norm_w0=wk, norm_w1=wk, norm_split=D,
+                         norm_cols=D, rope_cols=0)
+    ref2 = _heads_ref(a, w[: 2 * D], bias[: 2 * D], wk, wk, D, D, 0, rope)
+    assert rel_l2(out2, ref2) < 4e-3
+
+
+def _attn_ref(q, k, v, heads):
+    Sq, Sk = q.shape[0], k.shape[0]
+    qh = q.float().view(Sq, heads, 64).transpose(0, 1)
+    kh = k.float().view(Sk, heads, 64).transpose(0, 1)
+    vh = v.float().view(Sk, heads, 64).transpose(0, 1)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1)
+    return (p @ vh).transpose(0, 1).reshape(Sq, heads * 64)
+
+
+@pytest.mark.parametrize("Sq,Sk,heads", [(256, 128, 1), (256, 256, 2), (512, 512, 4), (300, 37, 3), (64, 24, 28),
+                                         (1000, 777, 2), (2048, 4096, 28)])
+def test_attention_dense(Sq, Sk, heads):
+    q, k, v = _rand((Sq, heads * 64), 20), _rand((Sk, heads * 64), 21), _rand((Sk, heads * 64), 22)
+    out = _ops().attention(q, k, v, heads)
+    ref = _attn_ref(q, k, v, heads)
+    # P is rounded to bf16 before P.V (as in flash-attn) and the output is bf16
+    assert rel_l2(out, ref) < 8e-3
+    assert float((out.float() - ref).abs().max()) < 0.05
+
+
+def test_attention_large_logits_lazy_rescale():
+    """Row maxima that keep growing along the KV axis exercise the lazy O rescale path."""
+    Sq, Sk, heads = 256, 1024, 2
+    q = _rand((Sq, heads * 64), 23, 2.0)
+    k = _rand((Sk, heads * 64), 24, 2.0) * torch.linspace(0.2, 3.0, Sk, device="cuda")[:, None].to(torch.bfloat16)
+    v = _rand((Sk, heads * 64), 25)
+    out = _ops().attention(q, k, v, heads)
+    assert rel_l2(out, _attn_ref(q, k, v, heads)) < 1e-2
+
+
+def test_attention_strided_views_of_fused_qkv():
+    S, heads = 640, 4
+    D = heads * 64
+    qkv = _rand((S, 3 * D), 26)
+    out = _ops().attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads)
+    ref = _attn_ref(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads)
+    assert rel_l2(out, ref) < 8e-3
+
+
+@pytest.mark.parametrize("S,D", [(1000, 1792), (37, 256), (8, 2048)])
+def test_ln_modulate(S, D):
+    x = _rand((S, D), 30, 2.0)
+    scale, shift = _rand((D,), 31, 0.3, torch.float32), _rand((D,), 32, 0.3, torch.float32)
+    out = _ops().ln_rows(x, scale, shift, plus_one=True)
+    ref = (torch.nn.functional.layer_norm(x.float(), (D,)) * (scale + 1.0) + shift).to(torch.bfloat16)   # nn.py:25-28
+    assert bf16_ulp_err(out, ref) <= 1.01
+    assert (out != ref).float().mean() < 0.01
+
+
+def test_invalid_arguments_raise_value_error():
+    a, w = _rand((64, 100), 40), _rand((64, 100), 41)          # K not a multiple of 8
+    with pytest.raises(ValueError):
+        _ops().linear(a, w)
