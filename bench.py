@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Headline benchmark: DiT denoising-step latency and latent-tokens/s of the Kandinsky-5 2B Lite DiT at
+768x512x121 (latent 31x64x96x16 -> S = 47 616 tokens, L = 256 text tokens), random-init weights, cached synthetic
+text embeddings (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl k5|reference] [--workload 5s_nocfg|5s_sft|10s_sft_nabla]
+
+A "step" is one iteration of the flow-matching sampler (generation_utils.py:105-128): one DiT forward (two with CFG)
+plus the Euler update.  `value` = visual tokens through the DiT per second with inputs resident in HBM; `e2e` = the
+same through the reference-facing API (DiffusionTransformer3D.forward -> C ABI) with pinned HOST buffers, H2D / D2H
+copies inside the timed region.  N > 1: one process per GPU (torchrun), every rank denoises its own video (the
+path shards by video; no data-path collective), value = all ranks' tokens / max-over-ranks time, scaling "weak".
+`--impl reference` times the reference algorithm's CPU path (the oracle port, oracle/dit_oracle.py) on the host
+cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "kandinsky-5_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+LITE = dict(in_visual_dim=16, out_visual_dim=16, time_dim=512, patch_size=(1, 2, 2), model_dim=1792, ff_dim=7168,
+            num_text_blocks=2, num_visual_blocks=32, axes_dims=(16, 24, 24), visual_cond=True, in_text_dim=3584,
+            in_text_dim2=768)
+WORKLOADS = {
+    # name: (latent T, H, W, text L, null L, guidance, scheduler_scale, nabla dict or None, NFE of the full config)
+    "5s_nocfg": dict(T=31, H=64, W=96, L=256, Ln=64, w=1.0, sched=5.0, nabla=None, nfe=50,
+                     name="config_5s_nocfg: 768x512x121, 50 NFE, no CFG"),
+    "5s_sft": dict(T=31, H=64, W=96, L=256, Ln=64, w=5.0, sched=5.0, nabla=None, nfe=100,
+                   name="config_5s_sft: 768x512x121, 50 steps x CFG = 100 NFE"),
+    "10s_sft_nabla": dict(T=61, H=64, W=96, L=256, Ln=64, w=5.0, sched=10.0,
+                          nabla=dict(P=0.9, wT=11, wH=3, wW=3, add_sta=True), nfe=100,
+                          name="config_10s_sft: 768x512x241, NABLA P=0.9 (11,3,3), 100 NFE"),
+}
+
+
+def dit_flops(S, L, rho=1.0, D=1792, F=7168, nvis=32, ntext=2):
+    """Algorithmic FLOPs of one forward."""
+    per_vis = (2 * S * D * 3 * D + 2 * S * D * D + 2 * S * D * D * 2 + 2 * L * D * 2 * D + 2 * S * D * F * 2
+               + rho * 4 * S * S * D + 4 * S * L * D + 2 * 512 * 9 * D)
+    per_text = 8 * L * D * D + 4 * L * D * F + 4 * L * L * D + 2 * 512 * 6 * D
+    return nvis * per_vis + ntext * per_text + 2 * S * 132 * D + 2 * L * 3584 * D + 2 * S * D * 64
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1386.8), d.get("bf16_tflops", 1642.7), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = f"/tmp/k5_clocks_{os.getpid()}.csv"
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_sample(wl, budget_s):
+    """Times the oracle port (the reference algorithm on the CPU, eager torch, all host threads) on a bounded sample
+    of the workload: ONE visual TransformerDecoderBlock (1/32 of the stack, >99.9 % of a forward's FLOPs are in the 32
+    blocks) for the first `Sq` query tokens against the full-length K/V, then extrapolates linearly in the query
+    count (every op of the block except the K/V projection is per query token) and x32 blocks."""
+    import torch
+
+    from oracle import dit_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(O.LITE_CFG, num_visual_blocks=1, num_text_blocks=0)
+    sd = {k: v for k, v in O.synthetic_state_dict(cfg, seed=0).items() if k.startswith("visual_transformer_blocks.0.")}
+    S = wl["T"] * (wl["H"] // 2) * (wl["W"] // 2)
+    L, D = wl["L"], cfg["model_dim"]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(S, D, generator=g).to(torch.bfloat16)
+    text = torch.randn(L, D, generator=g).to(torch.bfloat16)
+    tm = torch.randn(1, cfg["time_dim"], generator=g)
+    ang = torch.randn(S, 32, generator=g)
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    pfx = "visual_transformer_blocks.0."
+
+    def kv_part():
+        m = O.modulation(sd, pfx + "visual_modulation.", tm)
+        shift, scale, _ = torch.chunk(torch.chunk(m, 3, dim=-1)[0], 3, dim=-1)
+        xn = O.scale_shift_norm(x, scale, shift, "cuda")
+        p = pfx + "self_attention."
+        k = O._lin(xn, sd[p + "to_key.weight"], sd[p + "to_key.bias"], "cuda").reshape(S, -1, 64)
+        v = O._lin(xn, sd[p + "to_value.weight"], sd[p + "to_value.bias"], "cuda").reshape(S, -1, 64)
+        k = O.apply_rotary(O.rms_norm_heads(k, sd[p + "key_norm.weight"], "cuda"), cos, sin, "cuda")
+        return xn, k, v, m
+
+    def q_part(Sq, xn, k, v, m):
+        sa, ca, ff = torch.chunk(m, 3, dim=-1)
+        p = pfx + "self_attention."
+        xq = x[:Sq]
+        q = O._lin(xn[:Sq], sd[p + "to_query.weight"], sd[p + "to_query.bias"], "cuda").reshape(Sq, -1, 64)
+        q = O.apply_rotary(O.rms_norm_heads(q, sd[p + "query_norm.weight"], "cuda"), cos[:Sq], sin[:Sq], "cuda")
+        o = O.attention(q, k, v, "cuda")
+        o = O._lin(o, sd[p + "out_layer.weight"], sd[p + "out_layer.bias"], "cuda")
+        xq = O.gate_sum(xq, o, torch.chunk(sa, 3, dim=-1)[2], "cuda")
+        shift, scale, gate = torch.chunk(ca, 3, dim=-1)
+        o = O._cross_attention(sd, pfx + "cross_attention.", O.scale_shift_norm(xq, scale, shift, "cuda"), text, "cuda")
+        xq = O.gate_sum(xq, o, gate, "cuda")
+        shift, scale, gate = torch.chunk(ff, 3, dim=-1)
+        o = O.feed_forward(sd, pfx + "feed_forward.", O.scale_shift_norm(xq, scale, shift, "cuda"), "cuda")
+        return O.gate_sum(xq, o, gate, "cuda")
+
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        xn, k, v, m = kv_part()
+        t_kv = time.perf_counter() - t0
+        # calibrate the per-query cost on a small slice, then size the sample to the budget
+        Sq0 = min(S, 512)
+        t0 = time.perf_counter()
+        q_part(Sq0, xn, k, v, m)
+        per_q = (time.perf_counter() - t0) / Sq0
+        Sq = int(max(512, min(S, (budget_s - t_kv) / max(per_q, 1e-9))))
+        Sq = min(S, (Sq // 64) * 64)
+        t0 = time.perf_counter()
+        q_part(Sq, xn, k, v, m)
+        t_q = time.perf_counter() - t0
+    t_block = t_kv + t_q * (S / Sq)
+    fwd_per_step = 2 if abs(wl["w"] - 1.0) > 1e-6 else 1
+    t_step = 32 * t_block * fwd_per_step
+    sample = (f"1 visual decoder block of 32 (oracle port, eager torch CPU, bf16 operands): K/V path for all S={S} tokens "
+              f"({t_kv:.2f} s) + query path for the first {Sq} of {S} tokens ({t_q:.2f} s), extrapolated linearly in queries, "
+              f"x32 blocks x{fwd_per_step} forward(s) per step")
+    return S * fwd_per_step / t_step, t_step * 1e3, cores, sample
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    per_step_budget = max(4.0, min(30.0, 150.0 / max(total, 1)))
+    vals, ms = [], []
+    cores, sample = 1, ""
+    for i in range(total):
+        v, m, cores, sample = cpu_reference_sample(wl, per_step_budget)
+        if i >= args.warmup:
+            vals.append(v)
+            ms.append(m)
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "dit_latent_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["name"], "tokens": wl["T"] * (wl["H"] // 2) * (wl["W"] // 2), "text_tokens": wl["L"]},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def synthetic_state_dict_gpu(cfg, device, seed=0):
+    """Random-init checkpoint generated on the device (same distributions as oracle.synthetic_state_dict: nn.Linear
+    style uniform weights, modulation re-randomised with N(0, 0.02) because the reference zero-inits it)."""
+    import math
+
+    import torch
+
+    from kandinsky.models.dit import state_dict_shapes
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    shapes = state_dict_shapes(cfg)
+    sd = {}
+    for key, shape in shapes.items():
+        fp32 = ("modulation" in key) or key.startswith("time_embeddings.") or ("norm" in key)
+        if "modulation" in key:
+            t = torch.randn(shape, device=device, generator=g) * 0.02
+        elif key.endswith("norm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, device=device, generator=g)
+        elif key.endswith("norm.bias"):
+            t = 0.05 * torch.randn(shape, device=device, generator=g)
+        else:
+            fan_in = shape[1] if key.endswith(".weight") else shapes[key[:-4] + "weight"][1]
+            t = (torch.rand(shape, device=device, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        sd[key] = t if fp32 else t.to(torch.bfloat16)
+    return sd
+
+
+def run_k5(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from kandinsky import _lib
+    from kandinsky.generation_utils import generate
+    from kandinsky.models.dit import DiffusionTransformer3D
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the DiT hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+
+    T, H, W, L, Ln = wl["T"], wl["H"], wl["W"], wl["L"], wl["Ln"]
+    S = T * (H // 2) * (W // 2)
+    cfg_on = abs(wl["w"] - 1.0) > 1e-6
+    fwd_per_step = 2 if cfg_on else 1
+    model = DiffusionTransformer3D(**LITE, max_tokens=S, max_text_tokens=max(L, Ln))
+    sd = synthetic_state_dict_gpu(LITE, dev, seed=0)
+    model.load_state_dict(sd, assign=True)
+    model.to(dev)
+    del sd
+    torch.cuda.empty_cache()
+
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    text = torch.randn(L, 3584, device=dev, generator=g).to(torch.bfloat16)
+    pooled = torch.randn(1, 768, device=dev, generator=g).to(torch.bfloat16)
+    ntext = torch.randn(Ln, 3584, device=dev, generator=g).to(torch.bfloat16)
+    npooled = torch.randn(1, 768, device=dev, generator=g).to(torch.bfloat16)
+    noise = torch.randn(T, H, W, 16, device=dev, generator=torch.Generator(device=dev).manual_seed(6554))
+    pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+    att = {"type": "nabla", **wl["nabla"]} if wl["nabla"] else {"type": "flash"}
+    conf = {"metrics": {"scale_factor": (1.0, 2.0, 2.0)}, "model": {"dit_params": dict(LITE), "attention": att}}
+    te = {"text_embeds": text, "pooled_embed": pooled}
+    nte = {"text_embeds": ntext, "pooled_embed": npooled}
+
+    def sample(nsteps, start):
+        # the schedule of a K-step run; cost per step does not depend on t
+        return generate(model, dev, (T, H, W, 16), nsteps, te, nte, pos, torch.arange(L), torch.arange(Ln), wl["w"],
+                        wl["sched"], conf, noise=start)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) -------------------------------------------------------------------
+    sample(max(args.warmup, 3), noise)
+    barrier()
+    import ctypes
+
+    lib.k5_engine_attention_timing(model._engine, 1, None, None)
+    lib.k5_launch_count(1)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    latent = sample(args.steps, noise)
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.k5_launch_count(1))
+    att_ms, att_n = ctypes.c_double(0.0), ctypes.c_int64(0)
+    lib.k5_engine_attention_timing(model._engine, 0, ctypes.byref(att_ms), ctypes.byref(att_n))
+    density = model.last_sparse_density() if wl["nabla"] else 1.0
+    assert bool(torch.isfinite(latent).all()), "non-finite latent"
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * S * fwd_per_step / (ms_step * 1e-3)
+
+    # ---- end to end through the reference-facing API with host buffers (e2e) -----------------------------
+    h_img = torch.randn(T, H, W, 16).pin_memory()
+    h_text, h_pooled = text.cpu().pin_memory(), pooled.cpu().pin_memory()
+    h_ntext, h_npooled = ntext.cpu().pin_memory(), npooled.cpu().pin_memory()
+    h_out = torch.empty(T, H, W, 16, dtype=torch.bfloat16).pin_memory()
+    sparse = None
+    if wl["nabla"]:
+        sparse = {"to_fractal": True, **wl["nabla"]}
+    t1000 = torch.tensor([500.0])
+
+    def e2e_step():
+        x = h_img.to(dev, non_blocking=True)
+        v = model(x, h_text.to(dev, non_blocking=True), h_pooled.to(dev, non_blocking=True), t1000, pos, torch.arange(L),
+                  scale_factor=(1.0, 2.0, 2.0), sparse_params=sparse)
+        if cfg_on:
+            vu = model(x, h_ntext.to(dev, non_blocking=True), h_npooled.to(dev, non_blocking=True), t1000, pos,
+                       torch.arange(Ln), scale_factor=(1.0, 2.0, 2.0), sparse_params=sparse)
+            v = vu + wl["w"] * (v - vu)
+        h_out.copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = h_img.numel() * 4 + h_text.numel() * 2 + h_pooled.numel() * 2
+    if cfg_on:
+        h2d += h_ntext.numel() * 2 + h_npooled.numel() * 2
+    d2h = h_out.numel() * 2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sustained, burst, src = measured_peaks()
+    flops_fwd = dit_flops(S, L, density)
+    attn_flops = density * 4.0 * S * S * 1792
+    att_avg_ms = att_ms.value / max(att_n.value, 1)
+    achieved = attn_flops / (att_avg_ms * 1e-3) / 1e12 if att_n.value else None
+    line = {
+        "metric": "dit_latent_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["name"], "tokens": S, "text_tokens": L, "forwards_per_step": fwd_per_step,
+                   "model": "Kandinsky-5 T2V Lite DiT 2.0B (random init, modulation re-randomised)",
+                   "parallelism": f"{world} independent video(s), one per GPU" if world > 1 else "single GPU",
+                   "l2_policy": "per-step working set (>2 GB activations + 4 GB weights) exceeds the 126 MB L2",
+                   "nabla_density": density if wl["nabla"] else None},
+        "ms_per_forward": ms_step / fwd_per_step,
+        "model_tflops_per_forward": flops_fwd / 1e12,
+        "model_tflops_achieved": flops_fwd * fwd_per_step / (ms_step * 1e-3) / 1e12,
+        "model_frac_of_sustained_peak": flops_fwd * fwd_per_step / (ms_step * 1e-3) / 1e12 / sustained,
+        "gpu_launches": launches,
+        "clocks": clk,
+        "e2e": {"value": world * S * fwd_per_step / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "kandinsky.models.dit.DiffusionTransformer3D.forward -> k5_dit_forward (pinned host buffers)"},
+        "roofline": {"kernel": "attention_fwd_kernel (visual self-attention, tcgen05)", "bound": "tensor",
+                     "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                     "frac": (achieved / sustained) if achieved else None, "peak_source": f"{src} (sustained bf16 GEMM)",
+                     "flops_per_launch": attn_flops, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n.value),
+                     "share_of_step": att_ms.value / ms_total if ms_total else None, "traffic": None},
+    }
+    if not args.no_cpu_baseline:
+        v, m, cores, smp = cpu_reference_sample(wl, 20.0)
+        line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": smp}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="k5", choices=["k5", "reference"])
+    ap.add_argument("--workload", default="5s_nocfg", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_k5(args, wl)
+
+
+if __name__ == "__main__":
+    main()

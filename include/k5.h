@@ -108,6 +108,11 @@ int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, fl
 /* Number of kernels launched by this library since the counter was last reset (bench.py's gpu_launches). */
 int64_t k5_launch_count(int reset);
 
+/* CUDA-event timing of the dominant kernel (visual self-attention), on the stream it is launched on.
+ * Returns the accumulated duration and launch count recorded since the previous call (synchronises on the last
+ * recorded event), then enables / disables recording for subsequent forwards.  Used by bench.py's roofline. */
+int k5_engine_attention_timing(k5_engine* e, int enable, double* total_ms, int64_t* launches);
+
 /* Realised NABLA block density of the last sparse forward (selected / total 64x64 blocks, averaged over
  * blocks and heads); 1.0 if the last forward was dense.  Synchronises the stream it was produced on. */
 float k5_last_sparse_density(k5_engine* e);

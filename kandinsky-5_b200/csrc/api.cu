@@ -19,6 +19,7 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
 int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, const bf16* text, int L, const bf16* pooled,
                   const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st);
 float engine_density(Engine* e);
+int engine_timing(Engine* e, int enable, double* total_ms, int64_t* launches);
 int64_t launch_count(bool reset);
 void count_launch(int n);
 }  // namespace k5
@@ -77,6 +78,10 @@ int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, fl
                          static_cast<const bf16*>(text), L, static_cast<const bf16*>(pooled),
                          static_cast<const bf16*>(null_text), Ln, static_cast<const bf16*>(null_pooled), sparse,
                          static_cast<cudaStream_t>(stream));
+}
+int k5_engine_attention_timing(k5_engine* e, int enable, double* total_ms, int64_t* launches) {
+    K5_NEED(e);
+    return engine_timing(reinterpret_cast<Engine*>(e), enable, total_ms, launches);
 }
 int64_t k5_launch_count(int reset) { return launch_count(reset != 0); }
 float k5_last_sparse_density(k5_engine* e) { return e ? engine_density(reinterpret_cast<Engine*>(e)) : 1.0f; }

@@ -42,6 +42,7 @@ struct Bars {
     uint32_t tmem_slot;
 };
 
+template <bool SPARSE>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -54,8 +55,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int warp = threadIdx.x >> 5;
     const int n_qpairs = (p.Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * p.heads;
-    const int nkv = (p.Sk + KT - 1) / KT;
-    const int kv_rem = p.Sk - (nkv - 1) * KT;           // valid kv rows in the last tile (1..128)
+    const int nkv_dense = (p.Sk + KT - 1) / KT;
+    const int kv_rem = p.Sk - (nkv_dense - 1) * KT;     // valid kv rows in the last tile (1..128)
 
     if (warp == 8 && elect_one()) {
         tma_prefetch_desc(&tmQ);
@@ -101,14 +102,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         mbar_expect_tx(&B->q_full[a], TILE_BYTES);
                         tma_load_2d(sQ + a * TILE_BYTES, &tmQ, &B->q_full[a], h * HD, q0 + a * QT);
                     }
+                    const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
+                    const int32_t* pairs = SPARSE ? p.item_pairs + static_cast<size_t>(item) * p.max_pairs : nullptr;
                     for (int j = 0; j < nkv; ++j) {
+                        const int kv0 = (SPARSE ? pairs[j] : j) * KT;
                         uint8_t* sk = sKV + st * 2 * TILE_BYTES;
                         mbar_wait(&B->k_empty[st], ph ^ 1);
                         mbar_expect_tx(&B->k_full[st], TILE_BYTES);
-                        tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, j * KT);
+                        tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, kv0);
                         mbar_wait(&B->v_empty[st], ph ^ 1);
                         mbar_expect_tx(&B->v_full[st], TILE_BYTES);
-                        tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, j * KT);
+                        tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, kv0);
                         if (++st == KV_STAGES) {
                             st = 0;
                             ph ^= 1;
@@ -149,6 +153,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 };
 
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+                    const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
                     // S_a(0) = Q_a K_0^T
                     mbar_wait(&B->k_full[kst], kph);
                     for (int a = 0; a < 2; ++a) {
@@ -210,16 +215,47 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int row = (item % n_qpairs) * 2 * QT + a * QT + wq * 32 + lane;
             float m_used = -INFINITY;
             float l = 0.f;
+            bool started = false;
+            const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
+            const uint8_t* masks = SPARSE ? p.item_mask + static_cast<size_t>(item) * p.max_pairs : nullptr;
+            const int qblk2 = (a * 2 + (wq >> 1)) * 2;     // bit position of this warp's 64-row query block
             for (int j = 0; j < nkv; ++j, ++cnt) {
+                bool actL = true, actR = true;
+                if constexpr (SPARSE) {
+                    const uint32_t mb = masks[j];
+                    actL = (mb >> qblk2) & 1u;
+                    actR = (mb >> (qblk2 + 1)) & 1u;
+                }
                 mbar_wait(&B->s_full[a], cnt & 1);
                 tc_fence_after();
+                if (SPARSE && !actL && !actR) {
+                    // nothing selected for this warp's query block in this KV tile: P = 0
+                    uint32_t z[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) z[c] = 0u;
+                    tmem_st32(tS + 0, z);
+                    tmem_st32(tS + 32, z);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&B->p_ready[a]);
+                    continue;
+                }
                 uint32_t s[128];
                 tmem_ld32(tS + 0, s);
                 tmem_ld32(tS + 32, s + 32);
                 tmem_ld32(tS + 64, s + 64);
                 tmem_ld32(tS + 96, s + 96);
                 tmem_wait_ld();
-                if (j == nkv - 1 && kv_rem < KT) {
+                if constexpr (SPARSE) {
+                    if (!actL) {
+#pragma unroll
+                        for (int c = 0; c < 64; ++c) s[c] = 0xff800000u;
+                    }
+                    if (!actR) {
+#pragma unroll
+                        for (int c = 64; c < 128; ++c) s[c] = 0xff800000u;
+                    }
+                } else if (j == nkv - 1 && kv_rem < KT) {
 #pragma unroll
                     for (int c = 0; c < 128; ++c)
                         if (c >= kv_rem) s[c] = 0xff800000u;      // -inf
@@ -235,8 +271,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 float alpha = 1.0f;
                 bool need = false;
-                if (j == 0) {
+                if (!started) {
                     m_used = mx;
+                    started = true;
                 } else if ((mx - m_used) * sl2 > RESCALE_THRESHOLD) {
                     alpha = fast_exp2((m_used - mx) * sl2);
                     m_used = mx;
@@ -283,7 +320,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tc_fence_before();
             mbar_arrive(&B->o_free[a]);
             if (row < p.Sq) {
-                const float inv = 1.0f / l;
+                const float inv = l > 0.f ? 1.0f / l : 0.f;
                 uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.ldo + h * HD);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -306,16 +343,102 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
 }
 
+// Pre-pass for block-sparse attention: per (head, 256-row query item) the ascending list of 128-row KV tiles
+// that contain at least one selected 64x64 block for any of the item's 4 query blocks, plus the 8-bit
+// sub-block mask (bit qblk*2 + half).
+__global__ void __launch_bounds__(256)
+build_items_kernel(const int32_t* __restrict__ kv_count, const int32_t* __restrict__ kv_index, int nbq, int nbk,
+                   int n_qpairs, int max_pairs, int32_t* __restrict__ item_count, int32_t* __restrict__ item_pairs,
+                   uint8_t* __restrict__ item_mask) {
+    __shared__ uint8_t act[4][2048];
+    __shared__ int warp_counts[8];
+    const int qp = blockIdx.x, h = blockIdx.y;
+    const int item = h * n_qpairs + qp;
+    for (int t = threadIdx.x; t < 4 * 2048; t += blockDim.x) (&act[0][0])[t] = 0;
+    __syncthreads();
+    for (int r = 0; r < 4; ++r) {
+        const int qb = qp * 4 + r;
+        if (qb >= nbq) break;
+        const int n = kv_count[static_cast<size_t>(h) * nbq + qb];
+        const int32_t* src = kv_index + (static_cast<size_t>(h) * nbq + qb) * nbk;
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            const int b = src[t];
+            if (b >= 0 && b < nbk) act[r][b] = 1;
+        }
+    }
+    __syncthreads();
+    const int npairs = (nbk + 1) / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;
+    for (int c0 = 0; c0 < npairs; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        uint32_t m = 0;
+        if (c < npairs) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                m |= static_cast<uint32_t>(act[r][2 * c]) << (2 * r);
+                if (2 * c + 1 < nbk) m |= static_cast<uint32_t>(act[r][2 * c + 1]) << (2 * r + 1);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
+        if (lane == 0) warp_counts[warp] = __popc(bal);
+        __syncthreads();
+        int pre = 0, tot = 0;
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) pre += warp_counts[w];
+            tot += warp_counts[w];
+        }
+        if (m != 0) {
+            const int pos = base + pre + __popc(bal & ((1u << lane) - 1u));
+            item_pairs[static_cast<size_t>(item) * max_pairs + pos] = c;
+            item_mask[static_cast<size_t>(item) * max_pairs + pos] = static_cast<uint8_t>(m);
+        }
+        base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (base == 0) {   // cannot happen for valid NABLA lists; keep the pipeline protocol alive
+            item_pairs[static_cast<size_t>(item) * max_pairs] = 0;
+            item_mask[static_cast<size_t>(item) * max_pairs] = 0;
+            base = 1;
+        }
+        item_count[item] = base;
+    }
+}
+
+struct SparseWs {
+    int32_t* count = nullptr;
+    int32_t* pairs = nullptr;
+    uint8_t* mask = nullptr;
+    size_t items = 0, max_pairs = 0;
+};
+SparseWs g_sparse_ws;
+
+int ensure_sparse_ws(size_t items, size_t max_pairs) {
+    SparseWs& w = g_sparse_ws;
+    if (w.items >= items && w.max_pairs >= max_pairs) return K5_OK;
+    if (w.count) cudaFree(w.count);
+    if (w.pairs) cudaFree(w.pairs);
+    if (w.mask) cudaFree(w.mask);
+    w = SparseWs();
+    K5_CHECK_CUDA(cudaMalloc(&w.count, items * sizeof(int32_t)));
+    K5_CHECK_CUDA(cudaMalloc(&w.pairs, items * max_pairs * sizeof(int32_t)));
+    K5_CHECK_CUDA(cudaMalloc(&w.mask, items * max_pairs));
+    w.items = items;
+    w.max_pairs = max_pairs;
+    return K5_OK;
+}
+
 }  // namespace
 
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
                   cudaStream_t st) {
     K5_REQUIRE(Sq > 0 && Sk > 0 && heads > 0, "attention: empty problem");
-    if (kv_count || kv_index) {
-        set_last_error("attention: block-sparse KV lists are not implemented yet");
-        return K5_ERR_UNSUPPORTED;
-    }
+    const bool sparse = kv_count != nullptr;
+    K5_REQUIRE((kv_count == nullptr) == (kv_index == nullptr), "attention: kv_count and kv_index go together");
+    K5_REQUIRE(!sparse || (Sq % 64 == 0 && Sk % 64 == 0 && Sk / 64 <= 2048),
+               "attention: block-sparse mode needs Sq, Sk multiples of 64 and at most 2048 KV blocks");
     K5_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: pitches must be x8 elements");
     K5_REQUIRE((reinterpret_cast<uintptr_t>(O) & 15) == 0, "attention: output must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
@@ -324,7 +447,8 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
     static bool configured = false;
     if (!configured) {
-        K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         configured = true;
     }
     AttnParams p;
@@ -336,9 +460,28 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.ldo = ldo;
     p.kv_count = kv_count;
     p.kv_index = kv_index;
-    const int n_items = ((Sq + 2 * QT - 1) / (2 * QT)) * heads;
+    const int n_qpairs = (Sq + 2 * QT - 1) / (2 * QT);
+    const int n_items = n_qpairs * heads;
     const int grid = n_items < sm_count() ? n_items : sm_count();
-    attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    p.item_count = nullptr;
+    p.item_pairs = nullptr;
+    p.item_mask = nullptr;
+    p.max_pairs = 0;
+    if (sparse) {
+        const int nbq = Sq / 64, nbk = Sk / 64;
+        const int max_pairs = (nbk + 1) / 2;
+        K5_TRY(ensure_sparse_ws(n_items, max_pairs));
+        build_items_kernel<<<dim3(n_qpairs, heads), 256, 0, st>>>(kv_count, kv_index, nbq, nbk, n_qpairs, max_pairs,
+                                                                  g_sparse_ws.count, g_sparse_ws.pairs, g_sparse_ws.mask);
+        K5_CHECK_CUDA(cudaGetLastError());
+        p.item_count = g_sparse_ws.count;
+        p.item_pairs = g_sparse_ws.pairs;
+        p.item_mask = g_sparse_ws.mask;
+        p.max_pairs = max_pairs;
+        attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    } else {
+        attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    }
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }

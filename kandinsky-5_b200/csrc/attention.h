@@ -11,6 +11,11 @@ struct AttnParams {
     // optional block-sparse KV lists over 64x64 blocks (NABLA); null = dense
     const int32_t* kv_count;   // [heads, Sq/64]
     const int32_t* kv_index;   // [heads, Sq/64, Sk/64], first kv_count entries valid, ascending
+    // derived per-item lists (built by a pre-pass from kv_count / kv_index): item = head * n_qpairs + qpair
+    const int32_t* item_count; // [items]            number of 128-row KV tiles the item visits
+    const int32_t* item_pairs; // [items, max_pairs] KV tile ids (ascending)
+    const uint8_t* item_mask;  // [items, max_pairs] bit (qblk*2 + half): 64x64 sub-block selected
+    int max_pairs;
 };
 
 // O[Sq, heads*64] = softmax(Q K^T * softmax_scale) V per head, head_dim 64, non-causal.

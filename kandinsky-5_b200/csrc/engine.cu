@@ -86,6 +86,11 @@ struct Engine {
     bool last_sparse = false;
     cudaStream_t last_stream = nullptr;
 
+    // optional CUDA-event timing of the dominant kernel (visual self-attention) for bench.py's roofline
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;     // pairs (start, stop)
+    size_t ev_used = 0;
+
     // staging for load_tensor
     void* stage = nullptr;
     size_t stage_bytes = 0;
@@ -111,6 +116,7 @@ struct Engine {
         return K5_OK;
     }
     ~Engine() {
+        for (auto& v : ev) cudaEventDestroy(v);
         for (void* p : allocs) cudaFree(p);
         if (stage) cudaFree(stage);
     }
@@ -530,7 +536,13 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
         idx = e->kv_index;
     }
     count_launch(1);
+    const bool timed = e->timing && M == e->S && e->ev_used + 2 <= e->ev.size();
+    if (timed) K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used], st));
     K5_TRY(attention_fwd(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, att, D, M, M, e->heads, 0.125f, cnt, idx, st));
+    if (timed) {
+        K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used + 1], st));
+        e->ev_used += 2;
+    }
     return out_proj_gate(e, att, b.self.o, x, mod + 2 * D, M, st);
 }
 
@@ -677,6 +689,30 @@ float engine_density(Engine* e) {
     cudaStreamSynchronize(e->last_stream);
     cudaMemcpy(h, e->density_acc, sizeof(h), cudaMemcpyDeviceToHost);
     return h[1] > 0.f ? h[0] / h[1] : 1.0f;
+}
+
+int engine_timing(Engine* e, int enable, double* total_ms, int64_t* launches) {
+    // read back what was recorded so far (synchronises), then switch recording on / off
+    double tot = 0.0;
+    int64_t n = 0;
+    if (e->ev_used) {
+        K5_CHECK_CUDA(cudaEventSynchronize(e->ev[e->ev_used - 1]));
+        for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+            float ms = 0.f;
+            K5_CHECK_CUDA(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+            tot += ms;
+            ++n;
+        }
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    e->ev_used = 0;
+    e->timing = enable != 0;
+    if (e->timing && e->ev.empty()) {
+        e->ev.resize(2 * 4096);
+        for (auto& v : e->ev) K5_CHECK_CUDA(cudaEventCreate(&v));
+    }
+    return K5_OK;
 }
 
 Engine* engine_new(const k5_config* cfg, int* rc) {

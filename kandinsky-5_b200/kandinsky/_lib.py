@@ -39,6 +39,7 @@ SIGNATURES = {
                                POINTER(K5Sparse), c_void_p, c_void_p]),
     "k5_sample": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int,
                           c_void_p, POINTER(K5Sparse), c_void_p]),
+    "k5_engine_attention_timing": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
     "k5_launch_count": (c_int64, [c_int]),
     "k5_last_sparse_density": (c_float, [c_void_p]),
     "k5_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,

@@ -111,7 +111,7 @@ class DiffusionTransformer3D(nn.Module):
             _lib._lib.k5_engine_destroy(eng)
             self._engine = None
 
-    def _buffers(self):
+    def _ref_buffers(self):
         """The reference's non-persistent buffers (nn.py:49-51,107,129), computed the way it computes them."""
         cfg = self.cfg
         hd = sum(cfg["axes_dims"])
@@ -153,7 +153,7 @@ class DiffusionTransformer3D(nn.Module):
         with torch.cuda.device(self._device):
             for k, v in sd.items():
                 self._load_one(k, v)
-            for k, v in self._buffers().items():
+            for k, v in self._ref_buffers().items():
                 self._load_one(k, v)
             check(lib().k5_engine_finalize(self._engine))
 

@@ -1,0 +1,83 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/k5.h
+declares, the ctypes binding covers them all, and argument errors surface as the reference's exception types."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "k5.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(k5_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kandinsky import _lib
+
+    _lib.lib()
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (k5_[a-z0-9_]+)", out))
+    decl = declared_symbols()
+    assert len(decl) >= 15
+    assert not [s for s in decl if s not in exported]
+    assert sorted(_lib.SIGNATURES) == decl            # the binding covers the whole header, nothing else
+
+
+def test_library_is_sm100a_and_uses_tcgen05_tma():
+    from kandinsky import _lib
+
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):     # tcgen05.mma, TMA load, tcgen05.ld / st
+        assert mnemonic in sass
+    assert "HMMA.16816" not in sass                               # no legacy mma.sync path
+
+
+def test_version_and_error_channel_without_gpu():
+    from kandinsky import _lib
+
+    lib = _lib.lib()
+    assert lib.k5_version() == 100
+    # null arguments are rejected before any CUDA call
+    rc = lib.k5_engine_finalize(None)
+    assert rc == _lib.K5_ERR_INVALID
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    assert b"null argument" in lib.k5_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kandinsky-5_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath or "__pycache__" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt, f"{f} references oracle/"
+
+
+def test_state_dict_contract_matches_oracle_contract():
+    from kandinsky.models.dit import state_dict_shapes
+    from oracle import dit_oracle as O
+
+    assert state_dict_shapes(O.LITE_CFG) == O.dit_state_dict_shapes(O.LITE_CFG)
+
+
+def test_reference_yaml_configs_parse_unchanged():
+    ref = "/root/reference/configs"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present on this box")
+    from kandinsky.utils import load_conf
+
+    for name in sorted(os.listdir(ref)):
+        conf = load_conf(os.path.join(ref, name))
+        assert conf.model.dit_params.model_dim == 1792
+        assert conf.model.attention.type in ("flash", "nabla")
+        assert list(conf.metrics.scale_factor) == [1.0, 2.0, 2.0]

@@ -108,3 +108,23 @@ def test_forward_is_deterministic_and_linear_in_nothing():
     a = model(*args, scale_factor=(1.0, 2.0, 2.0))
     b = model(*args, scale_factor=(1.0, 2.0, 2.0))
     assert torch.equal(a, b)
+
+
+def test_nabla_forward_matches_reference_golden():
+    """NABLA path (fractal token order, adaptive block selection, block-sparse attention): (a) the engine's
+    output against the reference-minted golden, (b) its realised block density against the reference masks."""
+    rec = torch.load(os.path.join(GOLD, "tiny_nabla_4x16x16.pt"), weights_only=False)
+    cfg = rec["cfg"]
+    T, H, W, L = rec["T"], rec["H"], rec["W"], rec["L"]
+    model, _ = build_model(cfg, T * (H // 2) * (W // 2))
+    img, text, pooled = golden_inputs(rec)
+    pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+    nb = rec["nabla"]
+    sparse = {"to_fractal": True, "P": nb["P"], "wT": nb["wT"], "wH": nb["wH"], "wW": nb["wW"], "add_sta": True}
+    out = model(img.cuda(), text.cuda(), pooled.cuda(), torch.tensor([rec["t"] * 1000.0]).cuda(), pos, torch.arange(L),
+                scale_factor=rec["scale_factor"], sparse_params=sparse)
+    err = rel_l2(out, rec["out"])
+    dens, ref_dens = model.last_sparse_density(), float(rec["block_masks"].float().mean())
+    print(f"nabla: engine-vs-reference {err:.2e}  density {dens:.4f} (reference {ref_dens:.4f})")
+    assert err < 1.5e-2
+    assert abs(dens - ref_dens) < 0.01
