@@ -72,7 +72,7 @@ def nabla_select(q, k, heads, P, sta=None):
     S = q.shape[0]
     nb = S // 64
     cnt = torch.empty(heads, nb, device=q.device, dtype=torch.int32)
-    idx = torch.empty(heads, nb, nb, device=q.device, dtype=torch.int32)
+    idx = torch.zeros(heads, nb, nb, device=q.device, dtype=torch.int32)      # entries past kv_count stay 0
     ws = torch.empty(heads * nb * nb + 2 * nb * heads * 64, device=q.device, dtype=torch.float32)
     check(lib().k5_nabla_select(ptr(q), q.stride(0), ptr(k), k.stride(0), S, heads, float(P), ptr(sta), ptr(cnt), ptr(idx),
                                 ptr(ws), stream_ptr()))
