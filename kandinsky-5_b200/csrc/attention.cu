@@ -7,16 +7,23 @@
 // One persistent CTA per SM works on (head, 256-query-row) items, heads outermost so that the K/V of
 // one head (12 MB at S = 47 616) stay L2 resident while all CTAs sweep its query tiles.  Roles:
 //   warps 0-3 / 4-7 : softmax warpgroups for query tile 0 / 1 (thread = one query row, so row max / sum
-//                     need no shuffles); they read S from TMEM, write P = exp2(.) back to TMEM as bf16
-//                     (aliasing S), rescale O lazily (only when the running max grew by > 2^8), and
-//                     normalise + store O at the end;
+//                     need no shuffles); they pull S from TMEM into registers (and hand the S buffer
+//                     straight back to the tensor pipe), compute P = exp2(.) and write it as packed bf16
+//                     into a separate TMEM buffer, rescale O lazily (only when the running max grew by
+//                     > 2^8), and normalise + store O at the end;
 //   warp 8          : TMA producer (Q tiles once per item, K and V tiles through a 5-stage ring);
-//   warp 9          : tcgen05.mma issuer:  S_a = Q_a K_j^T (SS form, 128x128x64), O_a += P_a V_j
-//                     (TS form: A = P from TMEM, B = V MN-major from shared memory, 128x64x128);
-//   warp 10         : TMEM allocation (S0 S1 O0 O1 = 384 of 512 columns).
-// The two query tiles ping-pong: while one warpgroup does its exponentials the tensor pipe serves the
-// other, because the issue order is  PV_a(j), QK_a(j+1)  per tile a (the pipe executes in order, which
-// is also what makes aliasing P onto S safe).
+//   warp 9          : tcgen05.mma issuer, event driven:  S_a = Q_a K_j^T (SS form, 128x128x64) as soon as
+//                     the softmax warpgroup has S_a(j-1) in registers, O_a += P_a V_j (TS form: A = P from
+//                     TMEM, B = V MN-major from shared memory, 128x64x128) as soon as P_a(j) is written;
+//   warp 10         : TMEM allocation (S0 S1 O0 O1 P0 P1 = all 512 columns).
+// Because P does not alias S, QK(j+1) never waits for the exponentials of tile j: the next scores are
+// ready long before a warpgroup finishes P(j), so the MUFU / FMA pipes of the two warpgroups stay busy.
+// The exponentials are the bottleneck at head_dim 64 (16 384 per 128x128 tile = 1024 MUFU cycles against 512
+// tensor cycles), therefore a compile-time fraction of them is evaluated on the FMA pipe instead
+// (Cody-Waite split + degree-3 polynomial, rel. error 9e-5 < bf16 rounding of P), and the surrounding
+// arithmetic uses the packed fp32x2 forms (FFMA2 / FADD2) and the 3-input max to save issue slots.
+#include <cstdlib>
+
 #include "attention.h"
 #include "common.h"
 #include "ptx.cuh"
@@ -32,17 +39,40 @@ constexpr int TILE_BYTES = 128 * 64 * 2;
 constexpr int KV_STAGES = 5;
 constexpr int ATT_SMEM = 2 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + 1024 + 512;
 constexpr int ATT_THREADS = 384;
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320;
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320, TM_P0 = 384, TM_P1 = 448;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: P stays <= 2^8 before a rescale is forced
 
 struct Bars {
     uint64_t q_full[2], q_empty[2];
     uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
-    uint64_t s_full[2], p_ready[2], pv_done[2], o_free[2];
+    uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2], o_free[2];
     uint32_t tmem_slot;
 };
 
-template <bool SPARSE>
+// exp2 of a pair on the FMA / ALU pipes: x = floor(x) + f, 2^f by a degree-3 polynomial on [0,1), the integer
+// part goes straight into the exponent field.  Valid for x in [-126, 126]; smaller inputs are clamped (result
+// ~1e-38, i.e. zero for the purposes of a softmax).
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+    const float MAGIC = 12582912.0f;                    // 1.5 * 2^23: low mantissa bits hold floor(x)
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    const uint64_t x = pack_f32x2(x0, x1);
+    const uint64_t xr = add_rm_f32x2(x, pack_f32x2(MAGIC, MAGIC));
+    const uint64_t xi = sub_f32x2(xr, pack_f32x2(MAGIC, MAGIC));
+    const uint64_t f = sub_f32x2(x, xi);
+    uint64_t p = fma_f32x2(f, pack_f32x2(0.077119089663028717f, 0.077119089663028717f),
+                           pack_f32x2(0.227564394474029541f, 0.227564394474029541f));
+    p = fma_f32x2(p, f, pack_f32x2(0.695146143436431885f, 0.695146143436431885f));
+    p = fma_f32x2(p, f, pack_f32x2(1.0f, 1.0f));
+    float r0, r1, q0, q1;
+    unpack_f32x2(xr, r0, r1);
+    unpack_f32x2(p, q0, q1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+
+// NPOLY of every 8 element pairs take the polynomial path, the rest the MUFU.
+template <bool SPARSE, int NPOLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -68,6 +98,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mbar_init(&B->q_full[a], 1);
             mbar_init(&B->q_empty[a], 1);
             mbar_init(&B->s_full[a], 1);
+            mbar_init(&B->s_free[a], 128);
             mbar_init(&B->p_ready[a], 128);
             mbar_init(&B->pv_done[a], 1);
             mbar_init(&B->o_free[a], 128);
@@ -87,7 +118,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tmem_base = B->tmem_slot;
 
     if (warp >= 8) {
-        reg_dec<56>();
+        reg_dec<72>();   // pool = 384 x 168 registers: 8 warps x 216 + 4 warps x 72
         if (warp == 8) {
             // ===================== TMA producer =====================
             if (elect_one()) {
@@ -121,94 +152,120 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
             }
         } else if (warp == 9) {
-            // ===================== MMA issuer =====================
+            // ===================== MMA issuer (event driven) =====================
+            // Four in-order streams: QK and PV of query tile 0 and 1.  Tile number g counts KV tiles over all
+            // items of this CTA (identical for both query tiles).  Triggers:
+            //   QK_a(g): S_a free = softmax has S_a(g-1) in registers (s_free), K(g) landed, Q_a landed at j == 0
+            //   PV_a(g): P_a(g) written (p_ready), V(g) landed, O_a drained by the epilogue at j == 0
+            // Everything is polled (never a blocking wait) because the four streams share the K/V ring.
             if (elect_one()) {
                 constexpr uint32_t idesc_qk = umma_idesc_bf16(QT, KT, 0, 0);
                 constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);
                 const uint32_t tS[2] = {tmem_base + TM_S0, tmem_base + TM_S1};
                 const uint32_t tO[2] = {tmem_base + TM_O0, tmem_base + TM_O1};
+                const uint32_t tP[2] = {tmem_base + TM_P0, tmem_base + TM_P1};
                 const uint32_t sq_addr = smem_u32(sQ);
                 const uint32_t skv_addr = smem_u32(sKV);
-                int kst = 0, vst = 0;
-                uint32_t kph = 0, vph = 0;
-                uint32_t cnt = 0;           // kv tiles processed so far (same for both query tiles)
-                int i = 0;
 
-                auto issue_qk = [&](int a, int stage) {
-                    const uint32_t qa = sq_addr + a * TILE_BYTES;
-                    const uint32_t ka = skv_addr + stage * 2 * TILE_BYTES;
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        umma_ss(tS[a], umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024),
-                                idesc_qk, k != 0 ? 1u : 0u);
-                    umma_commit(&B->s_full[a]);
+                struct Stream {
+                    int item;       // current item id (>= n_items: finished)
+                    int i;          // items done by this stream
+                    int j, nkv;     // tile within the item
+                    uint32_t g;     // global tile counter
+                    int st;         // ring stage of tile g
+                    uint32_t ph;    // ring phase of tile g
                 };
-                auto issue_pv = [&](int a, int stage, bool accumulate) {
-                    const uint32_t va = skv_addr + stage * 2 * TILE_BYTES + TILE_BYTES;
-#pragma unroll
-                    for (int k = 0; k < KT / 16; ++k)
-                        umma_ts(tO[a], tS[a] + k * 8, umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
-                                (accumulate || k != 0) ? 1u : 0u);
-                    umma_commit(&B->pv_done[a]);
+                Stream qk[2], pv[2];
+                for (int a = 0; a < 2; ++a) {
+                    Stream s;
+                    s.item = blockIdx.x;
+                    s.i = 0;
+                    s.j = 0;
+                    s.nkv = s.item < n_items ? (SPARSE ? p.item_count[s.item] : nkv_dense) : 0;
+                    s.g = 0;
+                    s.st = 0;
+                    s.ph = 0;
+                    qk[a] = s;
+                    pv[a] = s;
+                }
+                auto advance = [&](Stream& s) {
+                    ++s.g;
+                    if (++s.st == KV_STAGES) {
+                        s.st = 0;
+                        s.ph ^= 1;
+                    }
+                    if (++s.j == s.nkv) {
+                        s.j = 0;
+                        ++s.i;
+                        s.item += gridDim.x;
+                        s.nkv = s.item < n_items ? (SPARSE ? p.item_count[s.item] : nkv_dense) : 0;
+                    }
                 };
-
-                for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
-                    const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
-                    // S_a(0) = Q_a K_0^T
-                    mbar_wait(&B->k_full[kst], kph);
+                int live = 4;
+                if (blockIdx.x >= n_items) live = 0;
+                uint32_t idle = 0;                       // consecutive polls without an issue: watchdog
+                while (live > 0) {
+                    if (++idle > K5_SPIN_LIMIT) __trap();
+#pragma unroll
                     for (int a = 0; a < 2; ++a) {
-                        mbar_wait(&B->q_full[a], i & 1);
-                        tc_fence_after();
-                        issue_qk(a, kst);
-                    }
-                    umma_commit(&B->k_empty[kst]);
-                    if (++kst == KV_STAGES) {
-                        kst = 0;
-                        kph ^= 1;
-                    }
-                    for (int j = 0; j < nkv; ++j, ++cnt) {
-                        mbar_wait(&B->v_full[vst], vph);
-                        for (int a = 0; a < 2; ++a) {
-                            if (j == 0) mbar_wait(&B->o_free[a], (i & 1) ^ 1);
-                            mbar_wait(&B->p_ready[a], cnt & 1);
-                            tc_fence_after();
-                            issue_pv(a, vst, j != 0);
-                            if (j + 1 < nkv) {
-                                if (a == 0) {
-                                    mbar_wait(&B->k_full[kst], kph);
-                                    tc_fence_after();
-                                }
-                                issue_qk(a, kst);
-                                if (a == 1) {
-                                    umma_commit(&B->k_empty[kst]);
-                                    if (++kst == KV_STAGES) {
-                                        kst = 0;
-                                        kph ^= 1;
-                                    }
-                                }
+                        // ---- QK_a
+                        Stream& s = qk[a];
+                        if (s.item < n_items) {
+                            bool ok = s.g == 0 || mbar_try_wait(&B->s_free[a], (s.g - 1) & 1);
+                            ok = ok && mbar_try_wait(&B->k_full[s.st], s.ph);
+                            ok = ok && (s.j != 0 || mbar_try_wait(&B->q_full[a], s.i & 1));
+                            if (ok) {
+                                tc_fence_after();
+                                const uint32_t qa = sq_addr + a * TILE_BYTES;
+                                const uint32_t ka = skv_addr + s.st * 2 * TILE_BYTES;
+#pragma unroll
+                                for (int k = 0; k < HD / 16; ++k)
+                                    umma_ss(tS[a], umma_desc_sw128(qa + k * 32, 0, 1024),
+                                            umma_desc_sw128(ka + k * 32, 0, 1024), idesc_qk, k != 0 ? 1u : 0u);
+                                umma_commit(&B->s_full[a]);
+                                if (qk[a ^ 1].g > s.g || qk[a ^ 1].item >= n_items) umma_commit(&B->k_empty[s.st]);
+                                if (s.j == s.nkv - 1) umma_commit(&B->q_empty[a]);
+                                advance(s);
+                                idle = 0;
+                                if (s.item >= n_items) --live;
                             }
                         }
-                        umma_commit(&B->v_empty[vst]);
-                        if (++vst == KV_STAGES) {
-                            vst = 0;
-                            vph ^= 1;
+                        // ---- PV_a
+                        Stream& t = pv[a];
+                        if (t.item < n_items) {
+                            bool ok = mbar_try_wait(&B->p_ready[a], t.g & 1);
+                            ok = ok && mbar_try_wait(&B->v_full[t.st], t.ph);
+                            ok = ok && (t.j != 0 || mbar_try_wait(&B->o_free[a], (t.i & 1) ^ 1));
+                            if (ok) {
+                                tc_fence_after();
+                                const uint32_t va = skv_addr + t.st * 2 * TILE_BYTES + TILE_BYTES;
+#pragma unroll
+                                for (int k = 0; k < KT / 16; ++k)
+                                    umma_ts(tO[a], tP[a] + k * 8, umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
+                                            (t.j != 0 || k != 0) ? 1u : 0u);
+                                umma_commit(&B->pv_done[a]);
+                                if (pv[a ^ 1].g > t.g || pv[a ^ 1].item >= n_items) umma_commit(&B->v_empty[t.st]);
+                                advance(t);
+                                idle = 0;
+                                if (t.item >= n_items) --live;
+                            }
                         }
                     }
-                    umma_commit(&B->q_empty[0]);
-                    umma_commit(&B->q_empty[1]);
                 }
             }
         }
     } else {
         // ===================== softmax warpgroups =====================
-        reg_inc<224>();
+        reg_inc<216>();
         const int a = warp >> 2;                          // query tile of this warpgroup
         const int wq = warp & 3;
         const int lane = threadIdx.x & 31;
         const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
         const uint32_t tS = tmem_base + (a == 0 ? TM_S0 : TM_S1) + lane_off;
         const uint32_t tO = tmem_base + (a == 0 ? TM_O0 : TM_O1) + lane_off;
+        const uint32_t tP = tmem_base + (a == 0 ? TM_P0 : TM_P1) + lane_off;
         const float sl2 = p.scale_log2;
+        const uint64_t sl2x2 = pack_f32x2(sl2, sl2);
         uint32_t cnt = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int h = item / n_qpairs;
@@ -229,12 +286,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 mbar_wait(&B->s_full[a], cnt & 1);
                 tc_fence_after();
                 if (SPARSE && !actL && !actR) {
-                    // nothing selected for this warp's query block in this KV tile: P = 0
+                    // nothing selected for this warp's query block in this KV tile: P = 0, S is not needed
+                    mbar_arrive(&B->s_free[a]);
+                    if (j > 0) {
+                        mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
+                        tc_fence_after();
+                    }
                     uint32_t z[32];
 #pragma unroll
                     for (int c = 0; c < 32; ++c) z[c] = 0u;
-                    tmem_st32(tS + 0, z);
-                    tmem_st32(tS + 32, z);
+                    tmem_st32(tP + 0, z);
+                    tmem_st32(tP + 32, z);
                     tmem_wait_st();
                     tc_fence_before();
                     mbar_arrive(&B->p_ready[a]);
@@ -246,6 +308,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tmem_ld32(tS + 64, s + 64);
                 tmem_ld32(tS + 96, s + 96);
                 tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&B->s_free[a]);              // the tensor pipe may overwrite S_a with the next scores
                 if constexpr (SPARSE) {
                     if (!actL) {
 #pragma unroll
@@ -262,11 +326,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 128; c += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s[c]));
-                    mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
-                    mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+                for (int c = 0; c < 128; c += 8) {
+                    mx0 = max3(mx0, __uint_as_float(s[c]), __uint_as_float(s[c + 1]));
+                    mx1 = max3(mx1, __uint_as_float(s[c + 2]), __uint_as_float(s[c + 3]));
+                    mx2 = max3(mx2, __uint_as_float(s[c + 4]), __uint_as_float(s[c + 5]));
+                    mx3 = max3(mx3, __uint_as_float(s[c + 6]), __uint_as_float(s[c + 7]));
                 }
                 const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 float alpha = 1.0f;
@@ -280,23 +344,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     need = true;
                 }
                 const float mneg = -m_used * sl2;
-                float sum0 = 0.f, sum1 = 0.f;
+                const uint64_t mnegx2 = pack_f32x2(mneg, mneg);
+                uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);
 #pragma unroll
                 for (int c = 0; c < 64; ++c) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * c]), sl2, mneg));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), sl2, mneg));
-                    sum0 += p0;
-                    sum1 += p1;
+                    // x = s * scale*log2(e) - m * scale*log2(e), both elements of the pair in one FFMA2
+                    const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])),
+                                                  sl2x2, mnegx2);
+                    float x0, x1, p0, p1;
+                    unpack_f32x2(x2, x0, x1);
+                    if ((c & 7) < NPOLY) {
+                        exp2_poly2(x0, x1, p0, p1);
+                    } else {
+                        p0 = fast_exp2(x0);
+                        p1 = fast_exp2(x1);
+                    }
+                    if (c & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));
+                    else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
                     s[c] = pack_bf16x2(p0, p1);              // P packed in place (c <= 2c)
                 }
-                l = l * alpha + (sum0 + sum1);
-                tmem_st32(tS + 0, s);
-                tmem_st32(tS + 32, s + 32);
-                tmem_wait_st();
-                if (j > 0 && __any_sync(0xffffffffu, need)) {
-                    // O_a holds the sum over tiles < j: wait for PV_a(j-1), then rescale this warp's rows.
+                {
+                    float t0, t1;
+                    unpack_f32x2(add_f32x2(sum_a, sum_b), t0, t1);
+                    l = l * alpha + (t0 + t1);
+                }
+                if (j > 0) {
+                    // PV_a(j-1) must have consumed the previous P (and produced the O this thread may rescale)
                     mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
                     tc_fence_after();
+                }
+                tmem_st32(tP + 0, s);
+                tmem_st32(tP + 32, s + 32);
+                if (j > 0 && __any_sync(0xffffffffu, need)) {
                     uint32_t o[64];
                     tmem_ld32(tO, o);
                     tmem_ld32(tO + 32, o + 32);
@@ -305,8 +384,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     for (int c = 0; c < 64; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
                     tmem_st32(tO, o);
                     tmem_st32(tO + 32, o + 32);
-                    tmem_wait_st();
                 }
+                tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&B->p_ready[a]);
             }
@@ -429,6 +508,37 @@ int ensure_sparse_ws(size_t items, size_t max_pairs) {
     return K5_OK;
 }
 
+constexpr int ATT_NPOLY_DEFAULT = 3;
+
+template <bool SPARSE>
+void launch_kernel(int npoly, int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                   const AttnParams& p, cudaStream_t st) {
+    switch (npoly) {
+        case 0: attention_fwd_kernel<SPARSE, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        case 2: attention_fwd_kernel<SPARSE, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        case 4: attention_fwd_kernel<SPARSE, 4><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        default: attention_fwd_kernel<SPARSE, 3><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    }
+}
+
+template <bool SPARSE, int NPOLY>
+int configure_one() {
+    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<SPARSE, NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ATT_SMEM));
+    return K5_OK;
+}
+int configure_kernels() {
+    K5_TRY((configure_one<false, 0>()));
+    K5_TRY((configure_one<false, 2>()));
+    K5_TRY((configure_one<false, 3>()));
+    K5_TRY((configure_one<false, 4>()));
+    K5_TRY((configure_one<true, 0>()));
+    K5_TRY((configure_one<true, 2>()));
+    K5_TRY((configure_one<true, 3>()));
+    K5_TRY((configure_one<true, 4>()));
+    return K5_OK;
+}
+
 }  // namespace
 
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
@@ -445,11 +555,13 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
-    static bool configured = false;
-    if (!configured) {
-        K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        configured = true;
+    static int npoly = -1;
+    if (npoly < 0) {
+        // fraction of the exponentials evaluated on the FMA pipe (pairs out of every 8); tuning knob only
+        const char* env = getenv("K5_ATTN_POLY");
+        npoly = env ? atoi(env) : ATT_NPOLY_DEFAULT;
+        if (npoly != 0 && npoly != 2 && npoly != 3 && npoly != 4) npoly = ATT_NPOLY_DEFAULT;
+        K5_TRY(configure_kernels());
     }
     AttnParams p;
     p.Sq = Sq;
@@ -478,9 +590,9 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         p.item_pairs = g_sparse_ws.pairs;
         p.item_mask = g_sparse_ws.mask;
         p.max_pairs = max_pairs;
-        attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+        launch_kernel<true>(npoly, grid, tmQ, tmK, tmV, p, st);
     } else {
-        attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+        launch_kernel<false>(npoly, grid, tmQ, tmK, tmV, p, st);
     }
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;

@@ -34,7 +34,8 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int XPOSE_BYTES = 4 * 32 * 128;   // per epilogue warp: 32 rows x 128 B, for the peer scatter
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XPOSE_BYTES;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -53,6 +54,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint8_t* xpose = smem + STAGES * Cfg::STAGE_BYTES + 256;
 
     const int warp = threadIdx.x >> 5;
     const int n_tiles_n = N / BN;
@@ -184,7 +186,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                     }
-                    if (row_ok) {
+                    if (e.peers.n > 0 && col0 >= e.peers.col0) {
+                        // K | V columns of a temporal shard: all-gather fused into the epilogue.  Transpose the
+                        // warp's 32 x 128 B through shared memory (XOR-swizzled 16-byte chunks, conflict free) so
+                        // that 8 lanes cover one 128-byte line, then store the lines to every rank's K|V buffer.
+                        uint4* xw = reinterpret_cast<uint4*>(xpose + wq * 4096);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            uint4 v;
+                            v.x = pack_bf16x2(x[8 * i + 0], x[8 * i + 1]);
+                            v.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
+                            v.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]);
+                            v.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
+                            xw[lane * 8 + (i ^ (lane & 7))] = v;
+                        }
+                        __syncwarp();
+                        const int chunk = lane & 7;
+                        uint4 v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 4 * i + (lane >> 3);
+                            v[i] = xw[r * 8 + (chunk ^ (r & 7))];
+                        }
+                        __syncwarp();
+                        const size_t colo = static_cast<size_t>(col0 - e.peers.col0) + chunk * 8;
+                        for (int pr = 0; pr < e.peers.n; ++pr) {
+                            bf16* base = e.peers.dst[pr];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rr = m0 + wq * 32 + 4 * i + (lane >> 3);
+                                if (rr < M)
+                                    *reinterpret_cast<uint4*>(base + (static_cast<size_t>(e.peers.row0) + rr) * e.peers.ld + colo) = v[i];
+                            }
+                        }
+                    } else if (row_ok) {
                         uint4* dst = reinterpret_cast<uint4*>(e.out + static_cast<size_t>(row) * e.ldo + col0);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -298,6 +333,10 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
         K5_REQUIRE(e.norm_cols % 64 == 0 && e.norm_split % 64 == 0 && e.rope_cols % 64 == 0, "GEMM: head split must be x64");
         K5_REQUIRE(e.norm_cols == 0 || (e.norm_w0 && e.norm_w1), "GEMM: head epilogue needs norm weights");
         K5_REQUIRE(e.rope_cols == 0 || e.rope, "GEMM: head epilogue needs a rope table");
+        K5_REQUIRE(e.peers.n >= 0 && e.peers.n <= MAX_PEERS, "GEMM: at most 8 scatter destinations");
+        K5_REQUIRE(e.peers.n == 0 || (e.peers.col0 % 64 == 0 && e.peers.ld % 8 == 0), "GEMM: scatter split must be x64");
+    } else {
+        K5_REQUIRE(e.peers.n == 0, "GEMM: the peer scatter belongs to the head epilogue");
     }
     const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
     CUtensorMap tmA, tmB;

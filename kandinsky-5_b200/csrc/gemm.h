@@ -5,6 +5,20 @@ namespace k5 {
 
 enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GATE = 2, EPI_HEADS = 3 };
 
+// Fused all-gather of the temporal shard (EPI_HEADS only): output columns >= col0 (the K | V part of the fused
+// QKV projection) are not written to `out` but to row (row0 + m), column (n - col0) of every destination in
+// dst[0..n) -- the [S, 2D] K|V buffers of all ranks of the node, peers mapped through CUDA IPC, own buffer
+// included.  The stores are plain st.global over NVLink, staged through shared memory so that every warp
+// instruction writes whole 128-byte lines.
+constexpr int MAX_PEERS = 8;
+struct PeerScatter {
+    bf16* dst[MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n = 0;
+    int ld = 0;
+    int col0 = 0;
+    long long row0 = 0;
+};
+
 struct GemmEpilogue {
     bf16* out = nullptr;            // [M, N] row-major, pitch ldo
     int ldo = 0;
@@ -21,6 +35,7 @@ struct GemmEpilogue {
     int norm_cols = 0;
     int rope_cols = 0;
     const float2* rope = nullptr;   // [M, 32] (cos, sin) per row and rotation pair
+    PeerScatter peers;              // n == 0: everything goes to `out`
 };
 
 // C[M,N] = A[M,K] . W[N,K]^T with a fused epilogue; A, W bf16 row-major (K contiguous).

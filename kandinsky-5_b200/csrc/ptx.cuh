@@ -50,8 +50,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Spin on an mbarrier phase.  A wait that outlives K5_SPIN_LIMIT polls (seconds; every legitimate wait in this
+// library is microseconds) traps, so a protocol bug surfaces as a CUDA error instead of a hung GPU.
+#ifndef K5_SPIN_LIMIT
+#define K5_SPIN_LIMIT (1u << 28)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > K5_SPIN_LIMIT) __trap();
     }
 }
 
@@ -174,6 +181,42 @@ __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+
+// ----------------------------------------------------------------------------- packed fp32x2 (sm_100 FFMA2 / FADD2)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_rm_f32x2(uint64_t a, uint64_t b) {   // round toward -inf
+    uint64_t r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
 template <uint32_t REGS>

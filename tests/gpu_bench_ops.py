@@ -31,7 +31,9 @@ def main():
     D, F = 1792, 7168
     dev = "cuda"
     torch.manual_seed(0)
-    for (M, N, K, epi) in [(S, 3 * D, D, "heads"), (S, D, D, "gate"), (S, F, D, "gelu"), (S, D, F, "gate"), (S, D, D, "store")]:
+    only = os.environ.get("K5_BENCH_ONLY", "")
+    gemms = [(S, 3 * D, D, "heads"), (S, D, D, "gate"), (S, F, D, "gelu"), (S, D, F, "gate"), (S, D, D, "store")]
+    for (M, N, K, epi) in ([] if only == "attn" else gemms):
         a = torch.randn(M, K, device=dev).bfloat16()
         w = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
@@ -49,9 +51,12 @@ def main():
     heads = 28
     qkv = torch.randn(S, 3 * D, device=dev).bfloat16()
     o = torch.empty(S, D, device=dev, dtype=torch.bfloat16)
-    ms = timeit(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads, out=o), iters=3, warm=1)
+    ms = timeit(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads, out=o), iters=5, warm=2)
     fl = 4.0 * S * S * D
-    line = f"attn S={S} h={heads}: k5 {ms:.2f} ms = {fl / ms / 1e9:.0f} TFLOP/s"
+    line = f"attn S={S} h={heads} poly={os.environ.get('K5_ATTN_POLY', 'default')}: k5 {ms:.2f} ms = {fl / ms / 1e9:.0f} TFLOP/s"
+    if only == "attn":
+        print(line, flush=True)
+        return
     try:
         from flash_attn import flash_attn_func
 

@@ -177,7 +177,10 @@ def test_sta_mask_matches_oracle():
 def _lists_to_mask(cnt, idx):
     h, nb, nk = idx.shape
     keep = torch.arange(nk, device=idx.device)[None, None, :] < cnt[..., None]
-    return torch.zeros(h, nb, nk, dtype=torch.bool, device=idx.device).scatter_(-1, idx.long(), keep)
+    # only the first kv_count entries of a row are defined (include/k5.h): park the rest on a spare column
+    safe = torch.where(keep, idx.long(), torch.full_like(idx, nk, dtype=torch.long))
+    assert int(safe.min()) >= 0 and int(safe.max()) <= nk
+    return torch.zeros(h, nb, nk + 1, dtype=torch.bool, device=idx.device).scatter_(-1, safe, keep)[..., :nk]
 
 
 @pytest.mark.parametrize("S,heads,P,use_sta", [(1024, 4, 0.6, True), (2048, 28, 0.9, False), (6144, 2, 0.5, True)])
