@@ -8,8 +8,10 @@ text embeddings (BASELINE.json).
 A "step" is one iteration of the flow-matching sampler (generation_utils.py:105-128): one DiT forward (two with CFG)
 plus the Euler update.  `value` = visual tokens through the DiT per second with inputs resident in HBM; `e2e` = the
 same through the reference-facing API (DiffusionTransformer3D.forward -> C ABI) with pinned HOST buffers, H2D / D2H
-copies inside the timed region.  N > 1: one process per GPU (torchrun), every rank denoises its own video (the
-path shards by video; no data-path collective), value = all ranks' tokens / max-over-ranks time, scaling "weak".
+copies inside the timed region.  N > 1: one process per GPU (torchrun), ONE video sharded along the latent's time
+axis: every rank owns a slab of frames, K | V are all-gathered per visual block inside the QKV
+projection kernel over NVLink peer memory (no NCCL on the data path; NCCL only returns the finished latent slabs once
+per sample), value = the video's tokens / max-over-ranks time, scaling "strong".
 `--impl reference` times the reference algorithm's CPU path (the oracle port, oracle/dit_oracle.py) on the host
 cores on a bounded sample of the same workload.
 """
@@ -267,7 +269,11 @@ def run_k5(args, wl):
     del sd
     torch.cuda.empty_cache()
 
-    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    if world > 1:
+        from kandinsky.models.parallelize import parallelize_dit
+
+        parallelize_dit(model)
+    g = torch.Generator(device=dev).manual_seed(1)          # identical inputs on every rank of the shard
     text = torch.randn(L, 3584, device=dev, generator=g).to(torch.bfloat16)
     pooled = torch.randn(1, 768, device=dev, generator=g).to(torch.bfloat16)
     ntext = torch.randn(Ln, 3584, device=dev, generator=g).to(torch.bfloat16)
@@ -316,7 +322,10 @@ def run_k5(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = world * S * fwd_per_step / (ms_step * 1e-3)
+    value = S * fwd_per_step / (ms_step * 1e-3)
+    model.set_grid((T, H, W), pos, (1.0, 2.0, 2.0), wl["nabla"] is not None)
+    f0, nf = model.local_frames()
+    S_loc = nf * (H // 2) * (W // 2)
 
     # ---- end to end through the reference-facing API with host buffers (e2e) -----------------------------
     h_img = torch.randn(T, H, W, 16).pin_memory()
@@ -336,7 +345,7 @@ def run_k5(args, wl):
             vu = model(x, h_ntext.to(dev, non_blocking=True), h_npooled.to(dev, non_blocking=True), t1000, pos,
                        torch.arange(Ln), scale_factor=(1.0, 2.0, 2.0), sparse_params=sparse)
             v = vu + wl["w"] * (v - vu)
-        h_out.copy_(v, non_blocking=True)
+        h_out[f0:f0 + nf].copy_(v[f0:f0 + nf], non_blocking=True)      # a rank produces (and returns) its own frames
         torch.cuda.synchronize()
 
     e2e_steps = max(2, min(args.steps, 5))
@@ -354,7 +363,7 @@ def run_k5(args, wl):
     h2d = h_img.numel() * 4 + h_text.numel() * 2 + h_pooled.numel() * 2
     if cfg_on:
         h2d += h_ntext.numel() * 2 + h_npooled.numel() * 2
-    d2h = h_out.numel() * 2
+    d2h = h_out[f0:f0 + nf].numel() * 2
 
     if rank != 0:
         if world > 1:
@@ -362,16 +371,23 @@ def run_k5(args, wl):
         return
     sustained, burst, src = measured_peaks()
     flops_fwd = dit_flops(S, L, density)
-    attn_flops = density * 4.0 * S * S * 1792
+    attn_flops = density * 4.0 * S_loc * S * 1792          # per launch on this rank: own query rows x all keys
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "attention_traffic.json")
+    if world == 1 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload)
     att_avg_ms = att_ms.value / max(att_n.value, 1)
     achieved = attn_flops / (att_avg_ms * 1e-3) / 1e12 if att_n.value else None
     line = {
         "metric": "dit_latent_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "tokens": S, "text_tokens": L, "forwards_per_step": fwd_per_step,
                    "model": "Kandinsky-5 T2V Lite DiT 2.0B (random init, modulation re-randomised)",
-                   "parallelism": f"{world} independent video(s), one per GPU" if world > 1 else "single GPU",
+                   "parallelism": (f"temporal shard x{world}: {nf} of {T} latent frames on rank 0, K|V all-gather fused into "
+                                   "the QKV GEMM epilogue over NVLink peer memory") if world > 1 else "single GPU",
                    "l2_policy": "per-step working set (>2 GB activations + 4 GB weights) exceeds the 126 MB L2",
                    "nabla_density": density if wl["nabla"] else None},
         "ms_per_forward": ms_step / fwd_per_step,
@@ -380,14 +396,14 @@ def run_k5(args, wl):
         "model_frac_of_sustained_peak": flops_fwd * fwd_per_step / (ms_step * 1e-3) / 1e12 / sustained,
         "gpu_launches": launches,
         "clocks": clk,
-        "e2e": {"value": world * S * fwd_per_step / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": S * fwd_per_step / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "kandinsky.models.dit.DiffusionTransformer3D.forward -> k5_dit_forward (pinned host buffers)"},
         "roofline": {"kernel": "attention_fwd_kernel (visual self-attention, tcgen05)", "bound": "tensor",
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                      "frac": (achieved / sustained) if achieved else None, "peak_source": f"{src} (sustained bf16 GEMM)",
                      "flops_per_launch": attn_flops, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n.value),
-                     "share_of_step": att_ms.value / ms_total if ms_total else None, "traffic": None},
+                     "share_of_step": att_ms.value / ms_total if ms_total else None, "traffic": traffic},
     }
     if not args.no_cpu_baseline:
         v, m, cores, smp = cpu_reference_sample(wl, 20.0)

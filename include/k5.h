@@ -105,6 +105,21 @@ int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, fl
               int L, const void* pooled, const void* null_text, int Ln, const void* null_pooled, const k5_sparse* sparse,
               void* stream);
 
+/* ---- temporal shard over the GPUs of one node -------------------------------------------
+ * The reference scales with a DTensor tensor-parallel plan (kandinsky/models/parallelize.py:11-102, entered from
+ * kandinsky/utils.py:40-87 when WORLD_SIZE > 1); these entry points replace it: one engine per rank, rank r owns a
+ * contiguous slab of latent frames, every per-token op is local, and the K | V rows of each visual block are
+ * all-gathered by the QKV projection itself (stores over NVLink into every rank's buffer) followed by one flag
+ * barrier.  Protocol: every rank calls k5_dist_export, the K5_DIST_HANDLE_BYTES blobs are exchanged by the host
+ * (torch.distributed.all_gather_object in the Python mirror), every rank calls k5_dist_init with all blobs in rank
+ * order, then k5_engine_set_grid.  All ranks must issue the same sequence of forwards.  In a shard, k5_dit_forward
+ * writes (and k5_sample integrates) only this rank's frames [first_frame, first_frame + num_frames) of out / img. */
+#define K5_DIST_HANDLE_BYTES 192
+int k5_dist_export(k5_engine* e, void* handle_out);
+int k5_dist_init(k5_engine* e, int rank, int world, const void* handles);
+int k5_dist_barrier(k5_engine* e, void* stream);
+int k5_dist_local_frames(k5_engine* e, int* first_frame, int* num_frames);
+
 /* Number of kernels launched by this library since the counter was last reset (bench.py's gpu_launches). */
 int64_t k5_launch_count(int reset);
 

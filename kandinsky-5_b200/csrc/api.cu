@@ -20,6 +20,10 @@ int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, co
                   const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st);
 float engine_density(Engine* e);
 int engine_timing(Engine* e, int enable, double* total_ms, int64_t* launches);
+int engine_dist_export(Engine* e, void* out);
+int engine_dist_init(Engine* e, int rank, int world, const void* handles);
+int engine_dist_barrier(Engine* e, cudaStream_t st);
+void engine_dist_info(Engine* e, int* f0, int* frames);
 int64_t launch_count(bool reset);
 void count_launch(int n);
 }  // namespace k5
@@ -82,6 +86,23 @@ int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, fl
 int k5_engine_attention_timing(k5_engine* e, int enable, double* total_ms, int64_t* launches) {
     K5_NEED(e);
     return engine_timing(reinterpret_cast<Engine*>(e), enable, total_ms, launches);
+}
+int k5_dist_export(k5_engine* e, void* handle_out) {
+    K5_NEED(e);
+    return engine_dist_export(reinterpret_cast<Engine*>(e), handle_out);
+}
+int k5_dist_init(k5_engine* e, int rank, int world, const void* handles) {
+    K5_NEED(e);
+    return engine_dist_init(reinterpret_cast<Engine*>(e), rank, world, handles);
+}
+int k5_dist_barrier(k5_engine* e, void* stream) {
+    K5_NEED(e);
+    return engine_dist_barrier(reinterpret_cast<Engine*>(e), static_cast<cudaStream_t>(stream));
+}
+int k5_dist_local_frames(k5_engine* e, int* first_frame, int* num_frames) {
+    K5_NEED(e);
+    engine_dist_info(reinterpret_cast<Engine*>(e), first_frame, num_frames);
+    return K5_OK;
 }
 int64_t k5_launch_count(int reset) { return launch_count(reset != 0); }
 float k5_last_sparse_density(k5_engine* e) { return e ? engine_density(reinterpret_cast<Engine*>(e)) : 1.0f; }

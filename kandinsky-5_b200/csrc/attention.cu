@@ -211,9 +211,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         // ---- QK_a
                         Stream& s = qk[a];
                         if (s.item < n_items) {
-                            bool ok = s.g == 0 || mbar_try_wait(&B->s_free[a], (s.g - 1) & 1);
-                            ok = ok && mbar_try_wait(&B->k_full[s.st], s.ph);
-                            ok = ok && (s.j != 0 || mbar_try_wait(&B->q_full[a], s.i & 1));
+                            bool ok = s.g == 0 || mbar_test_wait(&B->s_free[a], (s.g - 1) & 1);
+                            ok = ok && mbar_test_wait(&B->k_full[s.st], s.ph);
+                            ok = ok && (s.j != 0 || mbar_test_wait(&B->q_full[a], s.i & 1));
                             if (ok) {
                                 tc_fence_after();
                                 const uint32_t qa = sq_addr + a * TILE_BYTES;
@@ -233,9 +233,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         // ---- PV_a
                         Stream& t = pv[a];
                         if (t.item < n_items) {
-                            bool ok = mbar_try_wait(&B->p_ready[a], t.g & 1);
-                            ok = ok && mbar_try_wait(&B->v_full[t.st], t.ph);
-                            ok = ok && (t.j != 0 || mbar_try_wait(&B->o_free[a], (t.i & 1) ^ 1));
+                            bool ok = mbar_test_wait(&B->p_ready[a], t.g & 1);
+                            ok = ok && mbar_test_wait(&B->v_full[t.st], t.ph);
+                            ok = ok && (t.j != 0 || mbar_test_wait(&B->o_free[a], (t.i & 1) ^ 1));
                             if (ok) {
                                 tc_fence_after();
                                 const uint32_t va = skv_addr + t.st * 2 * TILE_BYTES + TILE_BYTES;

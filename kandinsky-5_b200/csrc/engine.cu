@@ -2,6 +2,9 @@
 // DiffusionTransformer3D.forward (kandinsky/models/dit.py:155-181) and the flow-matching sampler
 // (kandinsky/generation_utils.py:39-129) as a fixed sequence of the kernels in gemm.cu / attention.cu /
 // rowops.cu / nabla.cu on one stream.  No host synchronisation inside forward / sample.
+#include <unistd.h>
+
+#include <cstring>
 #include <map>
 #include <set>
 #include <string>
@@ -27,6 +30,27 @@ int64_t launch_count(bool reset) {
 namespace {
 
 constexpr float LN_EPS = 1e-5f;
+
+// ---- temporal shard: cross-GPU barrier on flags in peer memory --------------------------------------------
+// Thread p publishes this rank's epoch into slot `rank` of rank p's flag array (release, system scope: the K/V
+// rows the preceding GEMM epilogue stored into p's buffer are visible before the flag), then waits until rank
+// p's epoch has arrived in the local array.  A wait that outlives ~20 s traps instead of hanging the GPU.
+struct PeerFlags {
+    uint32_t* f[MAX_PEERS];
+};
+__global__ void dist_barrier_kernel(PeerFlags peers, uint32_t* mine, int rank, int world, uint32_t epoch) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.f[p] + rank), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + p) : "memory");
+        if (static_cast<int32_t>(v - epoch) >= 0) break;
+        if (clock64() - t0 > 40000000000LL) __trap();
+    }
+}
 
 struct Lin {
     bf16* W = nullptr;     // [out, ld] bf16
@@ -95,6 +119,23 @@ struct Engine {
     void* stage = nullptr;
     size_t stage_bytes = 0;
 
+    // temporal shard over the GPUs of one node (k5_dist_*): this rank owns frames [f0, f0 + Tl) = tokens
+    // [tok0, tok0 + Sl); K | V of all tokens are all-gathered per visual block into kv_all[buf]
+    struct Dist {
+        bool on = false;
+        int rank = 0, world = 1;
+        void* block = nullptr;            // one allocation: flags | kv_all[0] | kv_all[1]  (one IPC handle)
+        size_t block_bytes = 0;
+        uint32_t* flags = nullptr;
+        bf16* kv[2] = {nullptr, nullptr};
+        uint32_t* peer_flags[MAX_PEERS] = {};
+        bf16* peer_kv[2][MAX_PEERS] = {};
+        std::vector<void*> opened;
+        uint32_t epoch = 0;
+        int buf = 0;
+    } dist;
+    int f0 = 0, Tl = 0, tok0 = 0, Sl = 0;
+
     // grid
     int T = 0, Hp = 0, Wp = 0, S = 0, fractal = 0;
     bool grid_set = false;
@@ -116,6 +157,8 @@ struct Engine {
         return K5_OK;
     }
     ~Engine() {
+        for (void* p : dist.opened) cudaIpcCloseMemHandle(p);
+        if (dist.block) cudaFree(dist.block);
         for (auto& v : ev) cudaEventDestroy(v);
         for (void* p : allocs) cudaFree(p);
         if (stage) cudaFree(stage);
@@ -449,8 +492,107 @@ int engine_set_grid(Engine* e, int T, int H, int W, const int32_t* pt, const int
     e->Wp = Wp;
     e->S = static_cast<int>(S);
     e->fractal = fractal ? 1 : 0;
+    e->f0 = 0;
+    e->Tl = T;
+    if (e->dist.on) {
+        K5_REQUIRE(T >= e->dist.world, "set_grid: the temporal shard needs at least one frame per rank");
+        const int base = T / e->dist.world, rem = T % e->dist.world, r = e->dist.rank;
+        e->f0 = r * base + (r < rem ? r : rem);
+        e->Tl = base + (r < rem ? 1 : 0);
+    }
+    e->tok0 = e->f0 * Hp * Wp;
+    e->Sl = e->Tl * Hp * Wp;
     e->grid_set = true;
     return K5_OK;
+}
+
+// ---- temporal shard set-up (include/k5.h: k5_dist_export / k5_dist_init) ----------------------------------
+namespace {
+struct DistHandle {                 // K5_DIST_HANDLE_BYTES = 192
+    uint64_t base;                  // raw device pointer (valid inside the exporting process)
+    uint64_t bytes;
+    int64_t pid;
+    int32_t device;
+    int32_t pad[9];
+    cudaIpcMemHandle_t ipc;         // 64 bytes
+    uint8_t pad2[64];
+};
+static_assert(sizeof(DistHandle) == 192, "handle layout is part of the C ABI");
+constexpr size_t DIST_FLAG_BYTES = 1024;
+}  // namespace
+
+int engine_dist_export(Engine* e, void* out) {
+    K5_REQUIRE(out, "dist_export: null handle buffer");
+    if (!e->dist.block) {
+        const size_t kv_bytes = static_cast<size_t>(e->c.max_tokens) * 2 * e->D * sizeof(bf16);
+        e->dist.block_bytes = DIST_FLAG_BYTES + 2 * kv_bytes;
+        K5_CHECK_CUDA(cudaMalloc(&e->dist.block, e->dist.block_bytes));
+        K5_CHECK_CUDA(cudaMemset(e->dist.block, 0, DIST_FLAG_BYTES));
+        K5_CHECK_CUDA(cudaDeviceSynchronize());
+        e->dist.flags = static_cast<uint32_t*>(e->dist.block);
+        e->dist.kv[0] = reinterpret_cast<bf16*>(static_cast<uint8_t*>(e->dist.block) + DIST_FLAG_BYTES);
+        e->dist.kv[1] = reinterpret_cast<bf16*>(static_cast<uint8_t*>(e->dist.block) + DIST_FLAG_BYTES + kv_bytes);
+    }
+    DistHandle h;
+    memset(&h, 0, sizeof(h));
+    h.base = reinterpret_cast<uint64_t>(e->dist.block);
+    h.bytes = e->dist.block_bytes;
+    h.pid = static_cast<int64_t>(getpid());
+    int dev = 0;
+    K5_CHECK_CUDA(cudaGetDevice(&dev));
+    h.device = dev;
+    K5_CHECK_CUDA(cudaIpcGetMemHandle(&h.ipc, e->dist.block));
+    memcpy(out, &h, sizeof(h));
+    return K5_OK;
+}
+
+int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
+    K5_REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world, "dist_init: rank / world out of range (1..8)");
+    K5_REQUIRE(handles, "dist_init: null handles");
+    K5_REQUIRE(e->dist.block, "dist_init: call k5_dist_export first");
+    K5_REQUIRE(!e->dist.on, "dist_init: already initialised");
+    const DistHandle* hs = static_cast<const DistHandle*>(handles);
+    const size_t kv_bytes = static_cast<size_t>(e->c.max_tokens) * 2 * e->D * sizeof(bf16);
+    for (int p = 0; p < world; ++p) {
+        K5_REQUIRE(hs[p].bytes == e->dist.block_bytes, "dist_init: peers were created with a different max_tokens / model_dim");
+        uint8_t* base = nullptr;
+        if (p == rank) {
+            base = static_cast<uint8_t*>(e->dist.block);
+        } else if (hs[p].pid == static_cast<int64_t>(getpid())) {
+            base = reinterpret_cast<uint8_t*>(hs[p].base);      // engines of one process (tests): plain pointers
+        } else {
+            void* ptr = nullptr;
+            K5_CHECK_CUDA(cudaIpcOpenMemHandle(&ptr, hs[p].ipc, cudaIpcMemLazyEnablePeerAccess));
+            e->dist.opened.push_back(ptr);
+            base = static_cast<uint8_t*>(ptr);
+        }
+        e->dist.peer_flags[p] = reinterpret_cast<uint32_t*>(base);
+        e->dist.peer_kv[0][p] = reinterpret_cast<bf16*>(base + DIST_FLAG_BYTES);
+        e->dist.peer_kv[1][p] = reinterpret_cast<bf16*>(base + DIST_FLAG_BYTES + kv_bytes);
+    }
+    e->dist.rank = rank;
+    e->dist.world = world;
+    e->dist.on = world > 1;
+    e->dist.epoch = 0;
+    e->dist.buf = 0;
+    e->grid_set = false;            // the local slab depends on (rank, world)
+    return K5_OK;
+}
+
+int engine_dist_barrier(Engine* e, cudaStream_t st) {
+    if (!e->dist.on) return K5_OK;
+    PeerFlags pf;
+    for (int p = 0; p < MAX_PEERS; ++p) pf.f[p] = e->dist.peer_flags[p];
+    ++e->dist.epoch;
+    count_launch(1);
+    dist_barrier_kernel<<<1, 32, 0, st>>>(pf, e->dist.flags, e->dist.rank, e->dist.world, e->dist.epoch);
+    K5_CHECK_CUDA(cudaGetLastError());
+    return K5_OK;
+}
+
+void engine_dist_info(Engine* e, int* f0, int* frames) {
+    if (f0) *f0 = e->f0;
+    if (frames) *frames = e->Tl;
 }
 
 namespace {
@@ -513,8 +655,9 @@ int feed_forward(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* hid, const 
 }
 
 int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16* att, const float* mod, int M,
-                   const float2* rope, const k5_sparse* sp, cudaStream_t st) {
+                   const float2* rope, const k5_sparse* sp, bool visual, cudaStream_t st) {
     const int D = e->D;
+    const bool shard = visual && e->dist.on;
     count_launch(1);
     K5_TRY(ln_rows(x, D, xn, D, M, D, mod + D, mod, true, LN_EPS, st));
     GemmEpilogue g;
@@ -526,7 +669,25 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
     g.norm_cols = 2 * D;
     g.rope_cols = 2 * D;
     g.rope = rope;
+    const bf16 *kp = qkv + D, *vp = qkv + 2 * D;
+    int ldkv = 3 * D, Sk = M;
+    if (shard) {
+        // all-gather fused into the projection: the K | V columns of this rank's rows go straight from the GEMM
+        // epilogue into every rank's [S, 2D] buffer over NVLink; one flag barrier, then attention over all of S
+        const int buf = e->dist.buf;
+        e->dist.buf ^= 1;          // the other buffer may still be read by a slower rank's previous block
+        g.peers.n = e->dist.world;
+        for (int p = 0; p < e->dist.world; ++p) g.peers.dst[p] = e->dist.peer_kv[buf][p];
+        g.peers.ld = 2 * D;
+        g.peers.col0 = D;
+        g.peers.row0 = e->tok0;
+        kp = e->dist.kv[buf];
+        vp = e->dist.kv[buf] + D;
+        ldkv = 2 * D;
+        Sk = e->S;
+    }
     K5_TRY(lin_gemm(xn, D, b.self.qkv, M, EPI_HEADS, g, st));
+    if (shard) K5_TRY(engine_dist_barrier(e, st));
     const int32_t *cnt = nullptr, *idx = nullptr;
     if (sp) {
         count_launch(nabla_select_launches());
@@ -536,9 +697,9 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
         idx = e->kv_index;
     }
     count_launch(1);
-    const bool timed = e->timing && M == e->S && e->ev_used + 2 <= e->ev.size();
+    const bool timed = e->timing && visual && e->ev_used + 2 <= e->ev.size();
     if (timed) K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used], st));
-    K5_TRY(attention_fwd(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, att, D, M, M, e->heads, 0.125f, cnt, idx, st));
+    K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st));
     if (timed) {
         K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used + 1], st));
         e->ev_used += 2;
@@ -547,7 +708,7 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
 }
 
 int cross_attention(Engine* e, const Block& b, const bf16* text, int L, const float* mod, cudaStream_t st) {
-    const int D = e->D, M = e->S;
+    const int D = e->D, M = e->Sl;
     count_launch(1);
     K5_TRY(ln_rows(e->x, D, e->xn, D, M, D, mod + D, mod, true, LN_EPS, st));
     GemmEpilogue gq;                 // q = RMSNorm(to_query(x)); no RoPE (nn.py:343-349)
@@ -582,7 +743,10 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
     K5_REQUIRE(L > 0 && L <= e->c.max_text_tokens, "forward: text length out of range");
     K5_REQUIRE(!sp || e->fractal, "forward: NABLA needs the fractal token order (set_grid fractal=1)");
     K5_REQUIRE(!sp || e->S % 64 == 0, "forward: NABLA needs a token count divisible by 64");
-    const int D = e->D, Td = e->Td, S = e->S;
+    K5_REQUIRE(!(sp && e->dist.on), "forward: NABLA attention is not available on a temporal shard yet");
+    const int D = e->D, Td = e->Td;
+    const int S = e->Sl;                                   // rows this rank owns (all of them without a shard)
+    const size_t frame_in = static_cast<size_t>(e->Hp) * 2 * e->Wp * 2;   // latent pixels per frame
     if (sp) K5_TRY(ensure_nabla(e, sp));
     e->last_sparse = sp != nullptr;
     e->last_stream = st;
@@ -606,9 +770,10 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
         count_launch(1);
         K5_TRY(ln_rows(e->tproj, D, e->te, D, L, D, e->text_ln_w, e->text_ln_b, false, LN_EPS, st));
     }
-    {   // visual_embeddings (nn.py:81-96), rows written directly in engine token order
+    {   // visual_embeddings (nn.py:81-96), rows written directly in engine token order (own frames only)
         count_launch(1);
-        K5_TRY(patchify(x, Cx, e->Cin, e->T, e->Hp, e->Wp, e->fractal != 0, e->patchA, e->KP, st));
+        K5_TRY(patchify(x + static_cast<size_t>(e->f0) * frame_in * Cx, Cx, e->Cin, e->Tl, e->Hp, e->Wp, e->fractal != 0,
+                        e->patchA, e->KP, st));
         GemmEpilogue g;
         g.out = e->x;
         g.ldo = D;
@@ -625,20 +790,21 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
         K5_TRY(rope1d_table(e->args_text, 32, e->pos_dev + 4096, L, e->rope_t, st));
         rope_t = e->rope_t;
     }
-    // --- text transformer blocks (dit.py:33-44)
+    // --- text transformer blocks (dit.py:33-44): replicated on every rank of a shard
     for (const Block& b : e->tblocks) {
         const float* mod = e->modOut + b.mod_off;
-        K5_TRY(self_attention(e, b, e->te, e->ten, e->tqkv, e->tatt, mod, L, rope_t, nullptr, st));
+        K5_TRY(self_attention(e, b, e->te, e->ten, e->tqkv, e->tatt, mod, L, rope_t, nullptr, false, st));
         K5_TRY(feed_forward(e, b, e->te, e->ten, e->thid, mod + 3 * D, L, st));
     }
     // --- visual transformer blocks (dit.py:61-79)
+    const float2* rope_v = e->rope_v + static_cast<size_t>(e->tok0) * 32;
     for (const Block& b : e->vblocks) {
         const float* mod = e->modOut + b.mod_off;
-        K5_TRY(self_attention(e, b, e->x, e->xn, e->qkv, e->att, mod, S, e->rope_v, sp, st));
+        K5_TRY(self_attention(e, b, e->x, e->xn, e->qkv, e->att, mod, S, rope_v, sp, true, st));
         K5_TRY(cross_attention(e, b, e->te, L, mod + 3 * D, st));
         K5_TRY(feed_forward(e, b, e->x, e->xn, e->hid, mod + 6 * D, S, st));
     }
-    // --- after_blocks / OutLayer (dit.py:150-153, nn.py:374-400)
+    // --- after_blocks / OutLayer (dit.py:150-153, nn.py:374-400): own frames of `out`
     {
         const float* mod = e->modOut + e->out_mod_off;     // (shift, scale)
         count_launch(2);
@@ -647,7 +813,8 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
         g.out = e->y64;
         g.ldo = 64;
         K5_TRY(lin_gemm(e->xn, D, e->out_lin, S, EPI_STORE, g, st));
-        K5_TRY(unpatchify(e->y64, 64, e->T, e->Hp, e->Wp, e->fractal != 0, e->c.out_visual_dim, out, st));
+        K5_TRY(unpatchify(e->y64, 64, e->Tl, e->Hp, e->Wp, e->fractal != 0, e->c.out_visual_dim,
+                          out + static_cast<size_t>(e->f0) * frame_in * e->c.out_visual_dim, st));
     }
     return K5_OK;
 }
@@ -658,7 +825,10 @@ int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, co
     K5_REQUIRE(num_steps > 0 && img, "sample: bad arguments");
     const bool cfg = fabsf(w - 1.0f) > 1e-6f;
     K5_REQUIRE(!cfg || (ntext && npooled && Ln > 0), "sample: guidance needs the null-text embeddings");
-    const size_t n = static_cast<size_t>(e->S) * 64;   // T*H*W*16 latent elements
+    // T*H*W*16 latent elements; on a temporal shard only this rank's frames are integrated (the caller gathers
+    // the slabs once, after the last step: a forward never reads other ranks' latent frames)
+    const size_t n = static_cast<size_t>(e->Sl) * 64;
+    const size_t off = static_cast<size_t>(e->tok0) * 64;
     // timesteps (generation_utils.py:102-103): linspace(1, 0, N+1), t <- s t / (1 + (s - 1) t), all fp32 like torch
     std::vector<float> ts(num_steps + 1);
     for (int i = 0; i <= num_steps; ++i) {
@@ -671,14 +841,14 @@ int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, co
     for (int i = 0; i < num_steps; ++i) {
         const float t = ts[i], dt = ts[i + 1] - ts[i];
         K5_TRY(engine_forward(e, img, e->c.in_visual_dim, text, L, nullptr, pooled, t * 1000.0f, sp, e->v_c, st));
-        const bf16* v = e->v_c;
+        const bf16* v = e->v_c + off;
         if (cfg) {
             K5_TRY(engine_forward(e, img, e->c.in_visual_dim, ntext, Ln, nullptr, npooled, t * 1000.0f, sp, e->v_u, st));
             count_launch(1);
-            K5_TRY(cfg_combine(e->v_c, e->v_u, w, e->v_c, n, st));
+            K5_TRY(cfg_combine(e->v_c + off, e->v_u + off, w, e->v_c + off, n, st));
         }
         count_launch(1);
-        K5_TRY(euler_step(img, v, dt, n, st));
+        K5_TRY(euler_step(img + off, v, dt, n, st));
     }
     return K5_OK;
 }

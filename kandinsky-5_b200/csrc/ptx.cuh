@@ -50,6 +50,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a hardware-defined time; a poller that watches several
+// barriers must not).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Spin on an mbarrier phase.  A wait that outlives K5_SPIN_LIMIT polls (seconds; every legitimate wait in this
 // library is microseconds) traps, so a protocol bug surfaces as a CUDA error instead of a hung GPU.
 #ifndef K5_SPIN_LIMIT

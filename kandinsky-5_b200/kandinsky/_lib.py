@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libk5.so")
 
 K5_OK, K5_ERR_INVALID, K5_ERR_CUDA, K5_ERR_STATE, K5_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 EPI_STORE, EPI_GELU, EPI_GATE, EPI_HEADS = 0, 1, 2, 3
+DIST_HANDLE_BYTES = 192
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 
 
@@ -40,6 +41,10 @@ SIGNATURES = {
     "k5_sample": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int,
                           c_void_p, POINTER(K5Sparse), c_void_p]),
     "k5_engine_attention_timing": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "k5_dist_export": (c_int, [c_void_p, c_void_p]),
+    "k5_dist_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "k5_dist_barrier": (c_int, [c_void_p, c_void_p]),
+    "k5_dist_local_frames": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "k5_launch_count": (c_int64, [c_int]),
     "k5_last_sparse_density": (c_float, [c_void_p]),
     "k5_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,

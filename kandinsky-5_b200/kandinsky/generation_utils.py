@@ -6,6 +6,7 @@ import ctypes
 import torch
 
 from ._lib import K5Sparse, check, lib, ptr, stream_ptr
+from .models.parallelize import gather_frames
 
 
 def _get(conf, path):
@@ -98,7 +99,7 @@ def generate(model, device, shape, num_steps, text_embeds, null_text_embeds, vis
             check(lib().k5_sample(model._engine, ptr(img), int(num_steps), float(guidance_weight), float(scheduler_scale),
                                   ptr(text), text.shape[0], ptr(pooled), ptr(ntext), 0 if ntext is None else ntext.shape[0],
                                   ptr(npooled), ctypes.byref(sp) if sp is not None else None, stream_ptr()))
-        return img
+        return gather_frames(model, img)
     # generic path: same loop as the reference, one engine forward per call
     ts = timesteps(num_steps, scheduler_scale, device)
     steps = list(zip(ts[:-1], torch.diff(ts)))
@@ -117,7 +118,7 @@ def generate(model, device, shape, num_steps, text_embeds, null_text_embeds, vis
         v = get_velocity(model, model_input, time, text_embeds, null_text_embeds, visual_rope_pos, text_rope_pos,
                          null_text_rope_pos, guidance_weight, conf, sparse_params=sparse_params)
         img = img + timestep_diff * v
-    return img
+    return gather_frames(model, img) if hasattr(model, "_engine") else img
 
 
 def generate_sample(shape, caption, dit, vae, conf, text_embedder, num_steps=25, guidance_weight=5.0, scheduler_scale=1,

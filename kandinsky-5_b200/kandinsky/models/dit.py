@@ -87,6 +87,7 @@ class DiffusionTransformer3D(nn.Module):
         self._device = None
         self._grid_key = None
         self._pending = None          # CPU state dict kept until .to(cuda) creates the engine
+        self.dist_rank, self.dist_world = 0, 1
 
     # ---- engine lifetime -------------------------------------------------------------------------------
     def _create_engine(self, device):
@@ -176,6 +177,32 @@ class DiffusionTransformer3D(nn.Module):
 
     def eval(self):
         return self
+
+    # ---- temporal shard (include/k5.h k5_dist_*; replaces models/parallelize.py of the reference) -----------
+    def dist_export(self):
+        """Opaque handle (bytes) of this rank's K|V exchange buffer; exchange them between ranks, then dist_init."""
+        if self._engine is None:
+            raise RuntimeError("dist_export: the model must be on its CUDA device first")
+        buf = ctypes.create_string_buffer(_lib.DIST_HANDLE_BYTES)
+        with torch.cuda.device(self._device):
+            check(lib().k5_dist_export(self._engine, buf))
+        return buf.raw
+
+    def dist_init(self, rank, world, handles):
+        """handles: list of `world` blobs from dist_export, in rank order."""
+        if len(handles) != world or any(len(h) != _lib.DIST_HANDLE_BYTES for h in handles):
+            raise ValueError("dist_init: need one exported handle per rank")
+        blob = ctypes.create_string_buffer(b"".join(handles), world * _lib.DIST_HANDLE_BYTES)
+        with torch.cuda.device(self._device):
+            check(lib().k5_dist_init(self._engine, int(rank), int(world), blob))
+        self.dist_rank, self.dist_world = int(rank), int(world)
+        self._grid_key = None
+
+    def local_frames(self):
+        """(first_frame, num_frames) of the latent this rank owns for the current grid."""
+        f0, n = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().k5_dist_local_frames(self._engine, ctypes.byref(f0), ctypes.byref(n)))
+        return f0.value, n.value
 
     # ---- forward ---------------------------------------------------------------------------------------
     def set_grid(self, shape, visual_rope_pos, scale_factor, fractal):

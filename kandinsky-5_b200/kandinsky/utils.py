@@ -102,6 +102,17 @@ def get_T2V_pipeline(device_map: Union[str, torch.device, dict], resolution: int
         state_dict = load_file(path)
     dit.load_state_dict(state_dict, assign=True)
     dit = dit.to(device_map["dit"])
+    if world_size > 1:
+        # kandinsky/utils.py:40-45,80-87: the reference initialises NCCL and applies its tensor-parallel plan here;
+        # this engine shards the latent along time instead (models/parallelize.py)
+        import torch.distributed as dist
+
+        from .models.parallelize import parallelize_dit
+
+        if not dist.is_initialized():
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dit = parallelize_dit(dit)
     if text_embedder is None:
         raise FileNotFoundError("no text embedder: Qwen2.5-VL / CLIP checkpoints are not on disk; pass text_embedder=... "
                                 "(contract: .encode(texts, type_of_content) -> ({'text_embeds','pooled_embed'}, cu_seqlens))")
