@@ -12,7 +12,7 @@
 //                     into a separate TMEM buffer, rescale O lazily (only when the running max grew by
 //                     > 2^8), and normalise + store O at the end;
 //   warp 8          : TMA producer (Q tiles once per item, K and V tiles through a 5-stage ring);
-//   warp 9          : tcgen05.mma issuer, event driven:  S_a = Q_a K_j^T (SS form, 128x128x64) as soon as
+//   warp 9 / 11     : tcgen05.mma issuers for query tile 0 / 1:  S_a = Q_a K_j^T (SS form, 128x128x64) as soon as
 //                     the softmax warpgroup has S_a(j-1) in registers, O_a += P_a V_j (TS form: A = P from
 //                     TMEM, B = V MN-major from shared memory, 128x64x128) as soon as P_a(j) is written;
 //   warp 10         : TMEM allocation (S0 S1 O0 O1 P0 P1 = all 512 columns).
@@ -105,9 +105,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         for (int s = 0; s < KV_STAGES; ++s) {
             mbar_init(&B->k_full[s], 1);
-            mbar_init(&B->k_empty[s], 1);
+            mbar_init(&B->k_empty[s], 2);            // both issuers commit on a stage before it is refilled
             mbar_init(&B->v_full[s], 1);
-            mbar_init(&B->v_empty[s], 1);
+            mbar_init(&B->v_empty[s], 2);
         }
         fence_barrier_init();
     }
@@ -151,104 +151,67 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                 }
             }
-        } else if (warp == 9) {
-            // ===================== MMA issuer (event driven) =====================
-            // Four in-order streams: QK and PV of query tile 0 and 1.  Tile number g counts KV tiles over all
-            // items of this CTA (identical for both query tiles).  Triggers:
-            //   QK_a(g): S_a free = softmax has S_a(g-1) in registers (s_free), K(g) landed, Q_a landed at j == 0
-            //   PV_a(g): P_a(g) written (p_ready), V(g) landed, O_a drained by the epilogue at j == 0
-            // Everything is polled (never a blocking wait) because the four streams share the K/V ring.
+        } else if (warp == 9 || warp == 11) {
+            // ===================== MMA issuers: one warp per query tile =====================
+            // Per query tile a the order of events is fixed:  S_a(g) pulled into registers (s_free) -> QK_a(g+1);
+            // P_a(g) written (p_ready) -> PV_a(g); so each issuer simply blocks on the next event of its own tile.
+            // The two issuers share only the K / V ring: a stage is released when BOTH have committed their MMA on
+            // it (k_empty / v_empty are initialised with count 2).
             if (elect_one()) {
+                const int a = warp == 9 ? 0 : 1;
                 constexpr uint32_t idesc_qk = umma_idesc_bf16(QT, KT, 0, 0);
                 constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);
-                const uint32_t tS[2] = {tmem_base + TM_S0, tmem_base + TM_S1};
-                const uint32_t tO[2] = {tmem_base + TM_O0, tmem_base + TM_O1};
-                const uint32_t tP[2] = {tmem_base + TM_P0, tmem_base + TM_P1};
-                const uint32_t sq_addr = smem_u32(sQ);
+                const uint32_t tS = tmem_base + (a == 0 ? TM_S0 : TM_S1);
+                const uint32_t tO = tmem_base + (a == 0 ? TM_O0 : TM_O1);
+                const uint32_t tP = tmem_base + (a == 0 ? TM_P0 : TM_P1);
+                const uint32_t qa = smem_u32(sQ) + a * TILE_BYTES;
                 const uint32_t skv_addr = smem_u32(sKV);
+                int kst = 0, vst = 0;
+                uint32_t kph = 0, vph = 0;
+                uint32_t g = 0;                     // KV tiles handled so far (over all items)
+                int i = 0;
 
-                struct Stream {
-                    int item;       // current item id (>= n_items: finished)
-                    int i;          // items done by this stream
-                    int j, nkv;     // tile within the item
-                    uint32_t g;     // global tile counter
-                    int st;         // ring stage of tile g
-                    uint32_t ph;    // ring phase of tile g
-                };
-                Stream qk[2], pv[2];
-                for (int a = 0; a < 2; ++a) {
-                    Stream s;
-                    s.item = blockIdx.x;
-                    s.i = 0;
-                    s.j = 0;
-                    s.nkv = s.item < n_items ? (SPARSE ? p.item_count[s.item] : nkv_dense) : 0;
-                    s.g = 0;
-                    s.st = 0;
-                    s.ph = 0;
-                    qk[a] = s;
-                    pv[a] = s;
-                }
-                auto advance = [&](Stream& s) {
-                    ++s.g;
-                    if (++s.st == KV_STAGES) {
-                        s.st = 0;
-                        s.ph ^= 1;
-                    }
-                    if (++s.j == s.nkv) {
-                        s.j = 0;
-                        ++s.i;
-                        s.item += gridDim.x;
-                        s.nkv = s.item < n_items ? (SPARSE ? p.item_count[s.item] : nkv_dense) : 0;
+                auto issue_qk = [&](bool last_of_item) {
+                    mbar_wait(&B->k_full[kst], kph);
+                    tc_fence_after();
+                    const uint32_t ka = skv_addr + kst * 2 * TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_ss(tS, umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024), idesc_qk,
+                                k != 0 ? 1u : 0u);
+                    umma_commit(&B->s_full[a]);
+                    umma_commit(&B->k_empty[kst]);
+                    if (last_of_item) umma_commit(&B->q_empty[a]);
+                    if (++kst == KV_STAGES) {
+                        kst = 0;
+                        kph ^= 1;
                     }
                 };
-                int live = 4;
-                if (blockIdx.x >= n_items) live = 0;
-                uint32_t idle = 0;                       // consecutive polls without an issue: watchdog
-                while (live > 0) {
-                    if (++idle > K5_SPIN_LIMIT) __trap();
-#pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        // ---- QK_a
-                        Stream& s = qk[a];
-                        if (s.item < n_items) {
-                            bool ok = s.g == 0 || mbar_test_wait(&B->s_free[a], (s.g - 1) & 1);
-                            ok = ok && mbar_test_wait(&B->k_full[s.st], s.ph);
-                            ok = ok && (s.j != 0 || mbar_test_wait(&B->q_full[a], s.i & 1));
-                            if (ok) {
-                                tc_fence_after();
-                                const uint32_t qa = sq_addr + a * TILE_BYTES;
-                                const uint32_t ka = skv_addr + s.st * 2 * TILE_BYTES;
-#pragma unroll
-                                for (int k = 0; k < HD / 16; ++k)
-                                    umma_ss(tS[a], umma_desc_sw128(qa + k * 32, 0, 1024),
-                                            umma_desc_sw128(ka + k * 32, 0, 1024), idesc_qk, k != 0 ? 1u : 0u);
-                                umma_commit(&B->s_full[a]);
-                                if (qk[a ^ 1].g > s.g || qk[a ^ 1].item >= n_items) umma_commit(&B->k_empty[s.st]);
-                                if (s.j == s.nkv - 1) umma_commit(&B->q_empty[a]);
-                                advance(s);
-                                idle = 0;
-                                if (s.item >= n_items) --live;
-                            }
+                for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+                    const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
+                    // S_a(0) = Q_a K_0^T: needs Q_a and the S buffer (drained at the last tile of the previous item)
+                    mbar_wait(&B->q_full[a], i & 1);
+                    if (g > 0) mbar_wait(&B->s_free[a], (g - 1) & 1);
+                    issue_qk(nkv == 1);
+                    for (int j = 0; j < nkv; ++j, ++g) {
+                        if (j + 1 < nkv) {
+                            mbar_wait(&B->s_free[a], g & 1);
+                            issue_qk(j + 2 == nkv);
                         }
-                        // ---- PV_a
-                        Stream& t = pv[a];
-                        if (t.item < n_items) {
-                            bool ok = mbar_test_wait(&B->p_ready[a], t.g & 1);
-                            ok = ok && mbar_test_wait(&B->v_full[t.st], t.ph);
-                            ok = ok && (t.j != 0 || mbar_test_wait(&B->o_free[a], (t.i & 1) ^ 1));
-                            if (ok) {
-                                tc_fence_after();
-                                const uint32_t va = skv_addr + t.st * 2 * TILE_BYTES + TILE_BYTES;
+                        if (j == 0) mbar_wait(&B->o_free[a], (i & 1) ^ 1);
+                        mbar_wait(&B->p_ready[a], g & 1);
+                        mbar_wait(&B->v_full[vst], vph);
+                        tc_fence_after();
+                        const uint32_t va = skv_addr + vst * 2 * TILE_BYTES + TILE_BYTES;
 #pragma unroll
-                                for (int k = 0; k < KT / 16; ++k)
-                                    umma_ts(tO[a], tP[a] + k * 8, umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
-                                            (t.j != 0 || k != 0) ? 1u : 0u);
-                                umma_commit(&B->pv_done[a]);
-                                if (pv[a ^ 1].g > t.g || pv[a ^ 1].item >= n_items) umma_commit(&B->v_empty[t.st]);
-                                advance(t);
-                                idle = 0;
-                                if (t.item >= n_items) --live;
-                            }
+                        for (int k = 0; k < KT / 16; ++k)
+                            umma_ts(tO, tP + k * 8, umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
+                                    (j != 0 || k != 0) ? 1u : 0u);
+                        umma_commit(&B->pv_done[a]);
+                        umma_commit(&B->v_empty[vst]);
+                        if (++vst == KV_STAGES) {
+                            vst = 0;
+                            vph ^= 1;
                         }
                     }
                 }
@@ -267,6 +230,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float sl2 = p.scale_log2;
         const uint64_t sl2x2 = pack_f32x2(sl2, sl2);
         uint32_t cnt = 0;
+        if (a == 1 && p.stagger > 0) {
+            // The two warpgroups share the MUFU.  Started together they stay in lock-step (exp phases collide, the
+            // MUFU idles while both load / reduce / store); started half a tile apart they interleave and stay so.
+            const long long t0 = clock64();
+            while (clock64() - t0 < p.stagger) {
+            }
+        }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int h = item / n_qpairs;
             const int row = (item % n_qpairs) * 2 * QT + a * QT + wq * 32 + lane;
@@ -346,22 +316,42 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 const float mneg = -m_used * sl2;
                 const uint64_t mnegx2 = pack_f32x2(mneg, mneg);
                 uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);
+                // Software-pipelined over chunks of 8 pairs: while chunk c goes through the MUFU / polynomial, the
+                // scaled arguments of chunk c+1 are formed (FFMA2) and the results of chunk c-1 are summed and packed,
+                // so no instruction waits on a MUFU result that was issued less than ~16 instructions earlier.
+                uint64_t xn[8];                          // x = s * scale*log2(e) - m * scale*log2(e) of the next chunk
+                float pc[16], pp[16];                    // exp2 of the current / previous chunk
 #pragma unroll
-                for (int c = 0; c < 64; ++c) {
-                    // x = s * scale*log2(e) - m * scale*log2(e), both elements of the pair in one FFMA2
-                    const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])),
-                                                  sl2x2, mnegx2);
-                    float x0, x1, p0, p1;
-                    unpack_f32x2(x2, x0, x1);
-                    if ((c & 7) < NPOLY) {
-                        exp2_poly2(x0, x1, p0, p1);
-                    } else {
-                        p0 = fast_exp2(x0);
-                        p1 = fast_exp2(x1);
+                for (int q = 0; q < 8; ++q)
+                    xn[q] = fma_f32x2_v(pack_f32x2(__uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1])), sl2x2, mnegx2);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (c < 8) {
+                            float x0, x1;
+                            unpack_f32x2(xn[q], x0, x1);
+                            if (q < NPOLY) {
+                                exp2_poly2(x0, x1, pc[2 * q], pc[2 * q + 1]);
+                            } else {
+                                pc[2 * q] = ex2_v(x0);
+                                pc[2 * q + 1] = ex2_v(x1);
+                            }
+                            if (c < 7) {
+                                const int e = 16 * (c + 1) + 2 * q;
+                                xn[q] = fma_f32x2_v(pack_f32x2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), sl2x2,
+                                                    mnegx2);
+                            }
+                        }
+                        if (c > 0) {
+                            const uint64_t pr = pack_f32x2(pp[2 * q], pp[2 * q + 1]);
+                            if (q & 1) sum_b = add_f32x2_v(sum_b, pr);
+                            else sum_a = add_f32x2_v(sum_a, pr);
+                            s[8 * (c - 1) + q] = pack_bf16x2_v(pp[2 * q], pp[2 * q + 1]);   // P packed in place
+                        }
                     }
-                    if (c & 1) sum_b = add_f32x2(sum_b, pack_f32x2(p0, p1));
-                    else sum_a = add_f32x2(sum_a, pack_f32x2(p0, p1));
-                    s[c] = pack_bf16x2(p0, p1);              // P packed in place (c <= 2c)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) pp[q] = pc[q];
                 }
                 {
                     float t0, t1;
@@ -508,7 +498,8 @@ int ensure_sparse_ws(size_t items, size_t max_pairs) {
     return K5_OK;
 }
 
-constexpr int ATT_NPOLY_DEFAULT = 3;
+constexpr int ATT_NPOLY_DEFAULT = 0;
+constexpr int ATT_STAGGER_DEFAULT = 0;
 
 template <bool SPARSE>
 void launch_kernel(int npoly, int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
@@ -555,8 +546,10 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
-    static int npoly = -1;
+    static int npoly = -1, stagger = 0;
     if (npoly < 0) {
+        const char* sg = getenv("K5_ATTN_STAGGER");
+        stagger = sg ? atoi(sg) : ATT_STAGGER_DEFAULT;
         // fraction of the exponentials evaluated on the FMA pipe (pairs out of every 8); tuning knob only
         const char* env = getenv("K5_ATTN_POLY");
         npoly = env ? atoi(env) : ATT_NPOLY_DEFAULT;
@@ -579,6 +572,7 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.item_pairs = nullptr;
     p.item_mask = nullptr;
     p.max_pairs = 0;
+    p.stagger = stagger;
     if (sparse) {
         const int nbq = Sq / 64, nbk = Sk / 64;
         const int max_pairs = (nbk + 1) / 2;

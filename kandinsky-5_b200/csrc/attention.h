@@ -16,6 +16,7 @@ struct AttnParams {
     const int32_t* item_pairs; // [items, max_pairs] KV tile ids (ascending)
     const uint8_t* item_mask;  // [items, max_pairs] bit (qblk*2 + half): 64x64 sub-block selected
     int max_pairs;
+    int stagger;           // cycles query tile 1 starts behind query tile 0 (keeps the two exp phases apart)
 };
 
 // O[Sq, heads*64] = softmax(Q K^T * softmax_scale) V per head, head_dim 64, non-causal.

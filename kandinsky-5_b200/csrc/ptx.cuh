@@ -226,6 +226,28 @@ __device__ __forceinline__ uint64_t add_rm_f32x2(uint64_t a, uint64_t b) {   // 
     asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// Order-pinned variants (asm volatile keeps the statement order the source gives): used where the schedule is
+// laid out by hand so that MUFU results are consumed many instructions after they are issued.
+__device__ __forceinline__ float ex2_v(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint64_t fma_f32x2_v(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2_v(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_v(float lo, float hi) {
+    uint32_t r;
+    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
