@@ -132,6 +132,34 @@ int k5_engine_attention_timing(k5_engine* e, int enable, double* total_ms, int64
  * blocks and heads); 1.0 if the last forward was dense.  Synchronises the stream it was produced on. */
 float k5_last_sparse_density(k5_engine* e);
 
+/* ---- VAE decode (config 5) -----------------------------------------------------------------------------
+ *   k5_vae_create / k5_vae_load_tensor / k5_vae_finalize
+ *        <- build_vae(conf.model.vae): AutoencoderKLHunyuanVideo.from_pretrained(..., subfolder="vae",
+ *           torch_dtype=float16), kandinsky/models/vae.py:1276-1282; keys = the diffusers checkpoint's decoder.* and
+ *           post_quant_conv.* tensors, any of f32 / bf16 / f16
+ *   k5_vae_decode
+ *        <- vae.decode(z).sample, kandinsky/generation_utils.py:220-221 -> vae.py:880-906 (decode), 847-877 (_decode),
+ *           1144-1204 (_temporal_tiled_decode), 928-936 (blend_t), 682-696 (HunyuanVideoDecoder3D.forward)
+ * z: float32 [latent_channels, T, H, W] (the reference's NCTHW latent, batch 1), already divided by
+ * scaling_factor; out: bf16 [3, 4 (T - 1) + 1, 8 H, 8 W].  tile_frames / stride_frames: temporal tiling in SAMPLE
+ * frames as chosen by get_dec_optimal_tiling (vae.py:1246-1273; (17, 8) for 121 and 241 frames); tile_frames <= 0
+ * decodes in one piece.  Spatial tiling (only for sqrt(H W) > 900 pixels) is not part of the T2V path. */
+typedef struct k5_vae k5_vae;
+typedef struct k5_vae_config {
+    int32_t block_out_channels[4]; /* (128, 256, 512, 512) */
+    int32_t latent_channels;       /* 16 */
+    int32_t out_channels;          /* 3 */
+    int32_t max_tile_frames;       /* workspace bound: latent frames decoded at once (5 for the (17, 8) tiling) */
+    int32_t max_height;            /* workspace bound: latent height (64) */
+    int32_t max_width;             /* workspace bound: latent width (96) */
+} k5_vae_config;
+int k5_vae_create(const k5_vae_config* cfg, k5_vae** out);
+void k5_vae_destroy(k5_vae* v);
+int k5_vae_load_tensor(k5_vae* v, const char* key, const void* data, int dtype, const int64_t* shape, int ndim);
+int k5_vae_finalize(k5_vae* v);
+int k5_vae_decode(k5_vae* v, const float* z, int T, int H, int W, int tile_frames, int stride_frames, void* out,
+                  void* stream);
+
 /* ---- operator level ---------------------------------------------------------------------------------- */
 #define K5_EPI_STORE 0
 #define K5_EPI_GELU 1
@@ -161,6 +189,13 @@ int k5_nabla_select(const void* q, int ldq, const void* k, int ldk, int S, int h
                     int32_t* kv_count, int32_t* kv_index, float* workspace, void* stream);
 /* STA block mask (fast_sta_nabla): uint8 [T*Hb*Wb, T*Hb*Wb], row-major (t,h,w) block order. */
 int k5_sta_mask(int T, int Hb, int Wb, int wT, int wH, int wW, uint8_t* out, void* stream);
+
+/* Causal 3x3x3 convolution on channels-last bf16 (HunyuanVideoCausalConv3d, vae.py:125-163).  x: [T, H, W, Cin];
+ * w: the checkpoint layout [Cout, Cin, 3, 3, 3] in bf16; bias float32 [Cout]; resid (optional) / out: [T, H, W, Cout].
+ * Cin, Cout multiples of 64.  workspace: bf16 [(T + 2) (H + 2) (W + 2) Cin + 27 Cout Cin].  (Parity-test entry
+ * point: pads, repacks and convolves; the engine keeps repacked weights and fuses GroupNorm + SiLU into the pad.) */
+int k5_conv3d_causal(const void* x, int T, int H, int W, int Cin, const void* w, int Cout, const float* bias,
+                     const void* resid, void* out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,9 +4,17 @@
 #include "common.h"
 #include "gemm.h"
 #include "nabla.h"
+#include "conv3d.h"
 #include "rowops.h"
+#include "vae_ops.h"
 
 namespace k5 {
+struct Vae;
+Vae* vae_new(const k5_vae_config* cfg, int* rc);
+void vae_delete(Vae* e);
+int vae_load_tensor(Vae* e, const char* key, const void* data, int dtype, const int64_t* shape, int ndim);
+int vae_finalize(Vae* e);
+int vae_decode(Vae* e, const float* z, int T, int H, int W, int tile_frames, int stride_frames, bf16* out, cudaStream_t st);
 struct Engine;
 Engine* engine_new(const k5_config* cfg, int* rc);
 void engine_delete(Engine* e);
@@ -165,6 +173,53 @@ int k5_nabla_select(const void* q, int ldq, const void* k, int ldk, int S, int h
     return nabla_select(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, S, heads, P, sta, kv_count,
                         kv_index, workspace, nullptr, static_cast<cudaStream_t>(stream));
 }
+int k5_vae_create(const k5_vae_config* cfg, k5_vae** out) {
+    K5_NEED(cfg);
+    K5_NEED(out);
+    int rc = 0;
+    Vae* v = vae_new(cfg, &rc);
+    *out = reinterpret_cast<k5_vae*>(v);
+    return rc;
+}
+void k5_vae_destroy(k5_vae* v) {
+    if (v) vae_delete(reinterpret_cast<Vae*>(v));
+}
+int k5_vae_load_tensor(k5_vae* v, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+    K5_NEED(v);
+    return vae_load_tensor(reinterpret_cast<Vae*>(v), key, data, dtype, shape, ndim);
+}
+int k5_vae_finalize(k5_vae* v) {
+    K5_NEED(v);
+    return vae_finalize(reinterpret_cast<Vae*>(v));
+}
+int k5_vae_decode(k5_vae* v, const float* z, int T, int H, int W, int tile_frames, int stride_frames, void* out,
+                  void* stream) {
+    K5_NEED(v);
+    return vae_decode(reinterpret_cast<Vae*>(v), z, T, H, W, tile_frames, stride_frames, static_cast<bf16*>(out),
+                      static_cast<cudaStream_t>(stream));
+}
+
+int k5_conv3d_causal(const void* x, int T, int H, int W, int Cin, const void* w, int Cout, const float* bias,
+                     const void* resid, void* out, void* workspace, void* stream) {
+    K5_NEED(x);
+    K5_NEED(w);
+    K5_NEED(bias);
+    K5_NEED(out);
+    K5_NEED(workspace);
+    if (Cin % 64 != 0 || Cout % 64 != 0) {
+        set_last_error("conv3d: Cin and Cout must be multiples of 64");
+        return K5_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bf16* pad = static_cast<bf16*>(workspace);
+    bf16* wr = pad + static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * Cin;
+    count_launch(3);
+    K5_TRY(pad_gather(static_cast<const bf16*>(x), T, H, W, Cin, 1, 1, 1, nullptr, nullptr, nullptr, 32, false, pad, st));
+    K5_TRY(repack_conv_weight(w, 1, Cout, Cin, 27, Cin, wr, st));
+    return conv3d_causal(pad, T, H, W, Cin, wr, Cout, Cout, bias, static_cast<const bf16*>(resid), Cout,
+                         static_cast<bf16*>(out), Cout, st);
+}
+
 int k5_sta_mask(int T, int Hb, int Wb, int wT, int wH, int wW, uint8_t* out, void* stream) {
     K5_NEED(out);
     count_launch(1);

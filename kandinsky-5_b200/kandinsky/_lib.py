@@ -22,6 +22,11 @@ class K5Config(Structure):
     ]
 
 
+class K5VaeConfig(Structure):
+    _fields_ = [("block_out_channels", c_int32 * 4), ("latent_channels", c_int32), ("out_channels", c_int32),
+                ("max_tile_frames", c_int32), ("max_height", c_int32), ("max_width", c_int32)]
+
+
 class K5Sparse(Structure):
     _fields_ = [("P", c_float), ("wT", c_int32), ("wH", c_int32), ("wW", c_int32), ("add_sta", c_int32)]
 
@@ -45,6 +50,13 @@ SIGNATURES = {
     "k5_dist_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "k5_dist_barrier": (c_int, [c_void_p, c_void_p]),
     "k5_dist_local_frames": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "k5_vae_create": (c_int, [POINTER(K5VaeConfig), POINTER(c_void_p)]),
+    "k5_vae_destroy": (None, [c_void_p]),
+    "k5_vae_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64), c_int]),
+    "k5_vae_finalize": (c_int, [c_void_p]),
+    "k5_vae_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "k5_conv3d_causal": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "k5_launch_count": (c_int64, [c_int]),
     "k5_last_sparse_density": (c_float, [c_void_p]),
     "k5_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,

@@ -161,6 +161,10 @@ def run_case(mod, name, widths, zshape, tiling=None, seed=3):
 
 def main():
     mod = import_reference_vae()
+    import json
+
+    with open(os.path.join(HERE, "vae_temporal_tiling.json"), "w") as f:       # the reference's tiling table, as data
+        json.dump({str(k): list(v) for k, v in mod.OPT_TEMPORAL_TILING.items()}, f)
     # one un-tiled causal decode at the real decoder widths: 3 latent frames 8x8 -> 9 frames 64x64
     run_case(mod, "vae_full_width_3x8x8", (128, 256, 512, 512), (1, 16, 3, 8, 8))
     # temporal tiling + blending exactly as for the 5 s video ((17, 8): 5-latent-frame tiles, stride 2, blend 8 frames)

@@ -70,3 +70,24 @@ def test_blend_is_identity_on_equal_tiles():
     c = VO.blend_t(a, b.clone(), 8)
     # weights (1 - x/8) and x/8 are exact in bf16 and sum to 1: blending a frame with itself changes at most 1 ulp
     assert rel_l2(c[:, :, :8], a[:, :, -8:]) < 4e-3
+
+
+def test_mirror_tiling_table_and_checkpoint_contract_match_the_reference():
+    """Host logic of the engine-backed AutoencoderKLHunyuanVideo mirror: its tiling table equals the reference's
+    (stored as data by make_golden_vae.py) and its state-dict contract equals the oracle's (which was checked against
+    the reference module when the vectors were minted)."""
+    import json
+
+    from kandinsky.models.vae import OPT_TEMPORAL_TILING, AutoencoderKLHunyuanVideo, decoder_state_dict_shapes
+
+    with open(os.path.join(GOLD, "vae_temporal_tiling.json")) as f:
+        ref = {int(k): tuple(v) for k, v in json.load(f).items()}
+    assert OPT_TEMPORAL_TILING == ref
+    assert decoder_state_dict_shapes() == VO.decoder_shapes()
+    vae = AutoencoderKLHunyuanVideo()
+    assert vae.config.scaling_factor == VO.SCALING_FACTOR
+    assert vae.get_dec_optimal_tiling((1, 16, 31, 64, 96)) == ((1, 17, 512, 768), (8, 512, 768))     # 5 s video
+    assert vae.get_dec_optimal_tiling((1, 16, 61, 64, 96)) == ((1, 17, 512, 768), (8, 512, 768))     # 10 s video
+    assert vae.get_dec_optimal_tiling((1, 16, 3, 8, 8)) == ((1, 9, 64, 64), (9, 64, 64))             # small: one piece
+    with pytest.raises(RuntimeError):
+        vae.decode(torch.zeros(1, 16, 3, 8, 8))                                  # no engine: fails loudly, no CPU path
