@@ -239,6 +239,51 @@ def synthetic_state_dict_gpu(cfg, device, seed=0):
     return sd
 
 
+def time_vae_decode(latent, dev):
+    """vae.decode of the latent the sampler produced, as generate_sample does it (generation_utils.py:210-222), through
+    the engine-backed AutoencoderKLHunyuanVideo mirror with random-init fp16 weights.  One warm-up, one timed decode."""
+    import torch
+
+    from kandinsky.models.vae import AutoencoderKLHunyuanVideo, decoder_state_dict_shapes
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    shapes = decoder_state_dict_shapes()
+    sd = {}
+    for k, shp in shapes.items():
+        if "norm" in k:
+            t = (1.0 + 0.1 * torch.randn(shp, device=dev, generator=g)) if k.endswith("weight") else 0.05 * torch.randn(shp, device=dev, generator=g)
+        else:
+            wshape = shp if k.endswith("weight") else shapes[k[:-4] + "weight"]
+            fan_in = 1
+            for d in wshape[1:]:
+                fan_in *= d
+            t = (torch.rand(shp, device=dev, generator=g) * 2 - 1) / fan_in ** 0.5
+        sd[k] = t.half()
+    T, H, W, _ = latent.shape
+    vae = AutoencoderKLHunyuanVideo(max_latent=(5, H, W))
+    vae.load_state_dict(sd)
+    vae.to(dev)
+    del sd
+    z = (latent.reshape(1, T, H, W, -1) / vae.config.scaling_factor).permute(0, 4, 1, 2, 3).contiguous()
+    z = z / z.std().clamp_min(1e-6)              # random-init DiT latents are not unit-scale; keep activations finite
+    video = vae.decode(z).sample
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    video = vae.decode(z).sample
+    u8 = ((video.clamp(-1.0, 1.0) + 1.0) * 127.5).to(torch.uint8)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert bool(torch.isfinite(video.float()).all()), "non-finite video"
+    tiles = len(range(0, T - 4 + 1, 2)) if T > 5 else 1
+    tflop = 118.84 * tiles * (H * W) / (64 * 96)
+    sustained, _, src = measured_peaks()
+    return {"ms": ms, "tiles": tiles, "frames": int(u8.shape[2]), "height": int(u8.shape[3]), "width": int(u8.shape[4]),
+            "algorithmic_tflop": tflop, "tflops_achieved": tflop / ms * 1e3, "frac_of_sustained_peak": tflop / ms * 1e3 / sustained,
+            "peak_source": src, "api": "kandinsky.models.vae.AutoencoderKLHunyuanVideo.decode -> k5_vae_decode (+ uint8 conversion)"}
+
+
 def run_k5(args, wl):
     import torch
     import torch.distributed as dist
@@ -365,6 +410,11 @@ def run_k5(args, wl):
         h2d += h_ntext.numel() * 2 + h_npooled.numel() * 2
     d2h = h_out[f0:f0 + nf].numel() * 2
 
+    # ---- VAE decode of the sampled latent (BASELINE.json configs[4], decode leg): reported beside the DiT metric ----
+    vae_info = None
+    if world == 1 and not args.no_vae and not wl["nabla"]:
+        vae_info = time_vae_decode(latent, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -405,6 +455,8 @@ def run_k5(args, wl):
                      "flops_per_launch": attn_flops, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n.value),
                      "share_of_step": att_ms.value / ms_total if ms_total else None, "traffic": traffic},
     }
+    if vae_info is not None:
+        line["vae_decode"] = vae_info
     if not args.no_cpu_baseline:
         v, m, cores, smp = cpu_reference_sample(wl, 20.0)
         line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": smp}
@@ -421,6 +473,7 @@ def main():
     ap.add_argument("--impl", default="k5", choices=["k5", "reference"])
     ap.add_argument("--workload", default="5s_nocfg", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE-decode measurement that follows the DiT timing")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -99,37 +99,50 @@ __device__ __forceinline__ void gn_silu8(float* v, int c0, int cpg, const float*
     }
 }
 
+// One block per padded row (tp, hp): the source row pointer is resolved once, threads sweep (wp, 8-channel slot).
+// blockDim (256) is a multiple of the slots per position, so a thread keeps its slot and folds GroupNorm into one
+// FMA per element: y = x * a + b with a = rstd * gamma, b = beta - mean * a.
 __global__ void __launch_bounds__(256)
 pad_gather_kernel(const bf16* __restrict__ x, int Ts, int Hs, int Ws, int C, int ft, int fh, int fw, int T, int H, int W,
                   const float* __restrict__ mean_rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                   int cpg, int silu, bf16* __restrict__ out) {
     const int cg = C / 8;
-    const size_t total = static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * cg;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int slot = static_cast<int>(i % cg);
-        size_t pp = i / cg;
-        const int wp = static_cast<int>(pp % (W + 2));
-        pp /= (W + 2);
-        const int hp = static_cast<int>(pp % (H + 2));
-        const int tp = static_cast<int>(pp / (H + 2));
-        // replicate padding: clamp to the (up-sampled) volume
-        int t = tp - 2, h = hp - 1, w = wp - 1;
-        t = t < 0 ? 0 : t;
-        h = h < 0 ? 0 : (h >= H ? H - 1 : h);
+    const int hp = blockIdx.x % (H + 2), tp = blockIdx.x / (H + 2);
+    int t = tp - 2, h = hp - 1;
+    t = t < 0 ? 0 : t;                                        // replicate padding: clamp to the (up-sampled) volume
+    h = h < 0 ? 0 : (h >= H ? H - 1 : h);
+    const int ts = (ft == 1 || t == 0) ? t : 1 + (t - 1) / ft;  // nearest up-sampling; frame 0 is never repeated
+    const int hs = h / fh;
+    const uint4* src = reinterpret_cast<const uint4*>(x + (static_cast<size_t>(ts) * Hs + hs) * Ws * C);
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(blockIdx.x) * (W + 2) * C);
+    const int slot = threadIdx.x % cg;
+    float a[8], b[8];
+    if (mean_rstd) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = slot * 8 + j, g = c / cpg;
+            a[j] = __ldg(mean_rstd + 2 * g + 1) * __ldg(gamma + c);
+            b[j] = __ldg(beta + c) - __ldg(mean_rstd + 2 * g) * a[j];
+        }
+    }
+    const int n = (W + 2) * cg;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int w = i / cg - 1;
         w = w < 0 ? 0 : (w >= W ? W - 1 : w);
-        // nearest up-sampling: frame 0 maps to frame 0, frames 1.. are repeated ft times
-        const int ts = (ft == 1 || t == 0) ? t : 1 + (t - 1) / ft;
-        const int hs = h / fh, ws = w / fw;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(ts) * Hs + hs) * Ws + ws) * C) + slot);
+        const uint4 u = __ldg(src + static_cast<size_t>(w / fw) * cg + slot);
         uint4 o = u;
         if (mean_rstd) {
             float v[8];
             unpack8(u, v);
-            gn_silu8(v, slot * 8, cpg, mean_rstd, gamma, beta, silu != 0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = fmaf(v[j], a[j], b[j]);
+                if (silu) y = __fdividef(y, 1.0f + __expf(-y));
+                v[j] = y;
+            }
             o = pack8(v);
         }
-        reinterpret_cast<uint4*>(out)[i] = o;
+        dst[i] = o;
     }
 }
 
@@ -324,9 +337,9 @@ int pad_gather(const bf16* x, int Ts, int Hs, int Ws, int C, int ft, int fh, int
     K5_REQUIRE(C % 8 == 0 && (ft == 1 || ft == 2) && fh >= 1 && fw >= 1, "pad_gather: bad arguments");
     K5_REQUIRE(!mean_rstd || (gamma && beta && groups > 0 && C % groups == 0), "pad_gather: GroupNorm needs gamma / beta");
     const int T = ft == 1 ? Ts : 1 + (Ts - 1) * ft, H = Hs * fh, W = Ws * fw;
-    const size_t total = static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * (C / 8);
-    pad_gather_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, Ts, Hs, Ws, C, ft, fh, fw, T, H, W, mean_rstd, gamma, beta,
-                                                             mean_rstd ? C / groups : 1, silu ? 1 : 0, out);
+    K5_REQUIRE(256 % (C / 8) == 0, "pad_gather: channel count must be 8 * a divisor of 256");
+    pad_gather_kernel<<<(T + 2) * (H + 2), 256, 0, st>>>(x, Ts, Hs, Ws, C, ft, fh, fw, T, H, W, mean_rstd, gamma, beta,
+                                                         mean_rstd ? C / groups : 1, silu ? 1 : 0, out);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }

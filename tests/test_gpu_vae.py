@@ -99,9 +99,12 @@ def test_decode_is_deterministic_and_tiles_agree_with_oracle_schedule():
 def test_vae_rejects_bad_arguments():
     vae, _ = _build((64, 64, 128, 128), (5, 8, 8))
     with pytest.raises(ValueError):
-        vae.decode(torch.zeros(1, 8, 3, 8, 8).cuda())                            # wrong latent channel count
+        vae._decode(torch.zeros(1, 16, 3, 16, 16).cuda())                        # larger than the engine's workspace
     with pytest.raises(ValueError):
-        vae._decode(torch.zeros(1, 16, 3, 16, 16).cuda())                        # larger than the workspace
+        vae.decode(torch.zeros(1, 8, 3, 8, 8).cuda())                            # wrong latent channel count
+    vae.apply_tiling((1, 9, 64, 64), (9, 64, 64))
+    with pytest.raises(NotImplementedError):
+        vae._decode(torch.zeros(1, 16, 3, 16, 16).cuda())                        # would need spatial tiles
     from kandinsky.models.vae import AutoencoderKLHunyuanVideo
 
     v2 = AutoencoderKLHunyuanVideo(block_out_channels=(64, 64, 128, 128), max_latent=(5, 8, 8))
