@@ -113,6 +113,16 @@ def get_T2V_pipeline(device_map: Union[str, torch.device, dict], resolution: int
             torch.cuda.set_device(local_rank)
             dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local_rank}"))
         dit = parallelize_dit(dit)
+    if vae is None:
+        # kandinsky/utils.py:118-120: build_vae(conf.model.vae); the engine-backed decoder loads the same diffusers folder
+        vae_conf = conf.model.vae
+        if vae_path is not None:
+            vae_conf.checkpoint_path = vae_path
+        ck = vae_conf.checkpoint_path
+        if ck is not None and os.path.exists(os.path.join(ck, "vae", "diffusion_pytorch_model.safetensors")):
+            from .models.vae import build_vae
+
+            vae = build_vae(vae_conf).to(device_map["vae"])
     if text_embedder is None:
         raise FileNotFoundError("no text embedder: Qwen2.5-VL / CLIP checkpoints are not on disk; pass text_embedder=... "
                                 "(contract: .encode(texts, type_of_content) -> ({'text_embeds','pooled_embed'}, cu_seqlens))")
