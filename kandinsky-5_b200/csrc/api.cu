@@ -170,7 +170,7 @@ int k5_nabla_select(const void* q, int ldq, const void* k, int ldk, int S, int h
     K5_NEED(kv_index);
     K5_NEED(workspace);
     count_launch(nabla_select_launches());
-    return nabla_select(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, S, heads, P, sta, kv_count,
+    return nabla_select(static_cast<const bf16*>(q), ldq, S, static_cast<const bf16*>(k), ldk, S, heads, P, sta, 0, kv_count,
                         kv_index, workspace, nullptr, static_cast<cudaStream_t>(stream));
 }
 int k5_vae_create(const k5_vae_config* cfg, k5_vae** out) {

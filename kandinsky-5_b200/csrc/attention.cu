@@ -475,21 +475,17 @@ build_items_kernel(const int32_t* __restrict__ kv_count, const int32_t* __restri
     }
 }
 
-struct SparseWs {
-    int32_t* count = nullptr;
-    int32_t* pairs = nullptr;
-    uint8_t* mask = nullptr;
-    size_t items = 0, max_pairs = 0;
-};
-SparseWs g_sparse_ws;
+AttnSparseWs g_sparse_ws;
 
-int ensure_sparse_ws(size_t items, size_t max_pairs) {
-    SparseWs& w = g_sparse_ws;
+int ensure_sparse_ws(AttnSparseWs& w, size_t items, size_t max_pairs) {
     if (w.items >= items && w.max_pairs >= max_pairs) return K5_OK;
     if (w.count) cudaFree(w.count);
     if (w.pairs) cudaFree(w.pairs);
     if (w.mask) cudaFree(w.mask);
-    w = SparseWs();
+    w.count = nullptr;
+    w.pairs = nullptr;
+    w.mask = nullptr;
+    w.items = w.max_pairs = 0;
     K5_CHECK_CUDA(cudaMalloc(&w.count, items * sizeof(int32_t)));
     K5_CHECK_CUDA(cudaMalloc(&w.pairs, items * max_pairs * sizeof(int32_t)));
     K5_CHECK_CUDA(cudaMalloc(&w.mask, items * max_pairs));
@@ -534,7 +530,7 @@ int configure_kernels() {
 
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st) {
+                  cudaStream_t st, AttnSparseWs* ws_in) {
     K5_REQUIRE(Sq > 0 && Sk > 0 && heads > 0, "attention: empty problem");
     const bool sparse = kv_count != nullptr;
     K5_REQUIRE((kv_count == nullptr) == (kv_index == nullptr), "attention: kv_count and kv_index go together");
@@ -576,13 +572,14 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     if (sparse) {
         const int nbq = Sq / 64, nbk = Sk / 64;
         const int max_pairs = (nbk + 1) / 2;
-        K5_TRY(ensure_sparse_ws(n_items, max_pairs));
-        build_items_kernel<<<dim3(n_qpairs, heads), 256, 0, st>>>(kv_count, kv_index, nbq, nbk, n_qpairs, max_pairs,
-                                                                  g_sparse_ws.count, g_sparse_ws.pairs, g_sparse_ws.mask);
+        AttnSparseWs& ws = ws_in ? *ws_in : g_sparse_ws;
+        K5_TRY(ensure_sparse_ws(ws, n_items, max_pairs));
+        build_items_kernel<<<dim3(n_qpairs, heads), 256, 0, st>>>(kv_count, kv_index, nbq, nbk, n_qpairs, max_pairs, ws.count,
+                                                                  ws.pairs, ws.mask);
         K5_CHECK_CUDA(cudaGetLastError());
-        p.item_count = g_sparse_ws.count;
-        p.item_pairs = g_sparse_ws.pairs;
-        p.item_mask = g_sparse_ws.mask;
+        p.item_count = ws.count;
+        p.item_pairs = ws.pairs;
+        p.item_mask = ws.mask;
         p.max_pairs = max_pairs;
         launch_kernel<true>(npoly, grid, tmQ, tmK, tmV, p, st);
     } else {
@@ -590,6 +587,12 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     }
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
+}
+
+AttnSparseWs::~AttnSparseWs() {
+    if (count) cudaFree(count);
+    if (pairs) cudaFree(pairs);
+    if (mask) cudaFree(mask);
 }
 
 }  // namespace k5

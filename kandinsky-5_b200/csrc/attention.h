@@ -19,10 +19,20 @@ struct AttnParams {
     int stagger;           // cycles query tile 1 starts behind query tile 0 (keeps the two exp phases apart)
 };
 
+// Scratch of the block-sparse pre-pass (per-item KV tile lists).  Owned by the caller so that several engines of one
+// process can run concurrently on different streams; nullptr = a process-wide instance (single-stream callers only).
+struct AttnSparseWs {
+    int32_t* count = nullptr;
+    int32_t* pairs = nullptr;
+    uint8_t* mask = nullptr;
+    size_t items = 0, max_pairs = 0;
+    ~AttnSparseWs();
+};
+
 // O[Sq, heads*64] = softmax(Q K^T * softmax_scale) V per head, head_dim 64, non-causal.
 // Q/K/V/O are row-major token matrices whose head h occupies columns [h*64, h*64+64).
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st);
+                  cudaStream_t st, AttnSparseWs* ws = nullptr);
 
 }  // namespace k5

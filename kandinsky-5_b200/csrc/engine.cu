@@ -106,6 +106,7 @@ struct Engine {
     int32_t *kv_count = nullptr, *kv_index = nullptr;
     float* nabla_ws = nullptr;
     float* density_acc = nullptr;
+    AttnSparseWs sparse_ws;          // per-engine scratch of the block-sparse pre-pass
     int sta_key[6] = {0, 0, 0, 0, 0, 0};
     bool last_sparse = false;
     cudaStream_t last_stream = nullptr;
@@ -691,15 +692,16 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
     const int32_t *cnt = nullptr, *idx = nullptr;
     if (sp) {
         count_launch(nabla_select_launches());
-        K5_TRY(nabla_select(qkv, 3 * D, qkv + D, 3 * D, M, e->heads, sp->P, sp->add_sta ? e->sta : nullptr, e->kv_count,
-                            e->kv_index, e->nabla_ws, e->density_acc, st));
+        // local query blocks against ALL key blocks (on a shard: the gathered K); STA rows of this rank's blocks
+        K5_TRY(nabla_select(qkv, 3 * D, M, kp, ldkv, Sk, e->heads, sp->P, sp->add_sta ? e->sta : nullptr, e->tok0 / 64,
+                            e->kv_count, e->kv_index, e->nabla_ws, e->density_acc, st));
         cnt = e->kv_count;
         idx = e->kv_index;
     }
     count_launch(1);
     const bool timed = e->timing && visual && e->ev_used + 2 <= e->ev.size();
     if (timed) K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used], st));
-    K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st));
+    K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st, &e->sparse_ws));
     if (timed) {
         K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used + 1], st));
         e->ev_used += 2;
@@ -742,8 +744,8 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
     K5_REQUIRE(Cx == e->Cin || Cx == e->c.in_visual_dim, "forward: x must have model-input or latent channel count");
     K5_REQUIRE(L > 0 && L <= e->c.max_text_tokens, "forward: text length out of range");
     K5_REQUIRE(!sp || e->fractal, "forward: NABLA needs the fractal token order (set_grid fractal=1)");
-    K5_REQUIRE(!sp || e->S % 64 == 0, "forward: NABLA needs a token count divisible by 64");
-    K5_REQUIRE(!(sp && e->dist.on), "forward: NABLA attention is not available on a temporal shard yet");
+    K5_REQUIRE(!sp || (e->S % 64 == 0 && e->Sl % 64 == 0 && e->tok0 % 64 == 0),
+               "forward: NABLA needs token counts (per frame, too, on a shard) divisible by 64");
     const int D = e->D, Td = e->Td;
     const int S = e->Sl;                                   // rows this rank owns (all of them without a shard)
     const size_t frame_in = static_cast<size_t>(e->Hp) * 2 * e->Wp * 2;   // latent pixels per frame

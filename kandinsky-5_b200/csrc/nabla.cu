@@ -48,9 +48,9 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 
 // One (head, query block) row per thread block.
 __global__ void __launch_bounds__(SEL_THREADS)
-nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int nb, int heads, float need,
-                 const uint8_t* __restrict__ sta, int32_t* __restrict__ kv_count, int32_t* __restrict__ kv_index,
-                 float* __restrict__ density_acc) {
+nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int nbq, int nb, int heads, float need,
+                 const uint8_t* __restrict__ sta, int sta_row0, int32_t* __restrict__ kv_count,
+                 int32_t* __restrict__ kv_index, float* __restrict__ density_acc) {
     __shared__ float key[NB_MAX];
     __shared__ uint16_t idx[NB_MAX];
     __shared__ float scan[NB_MAX];
@@ -148,10 +148,10 @@ nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int n
     __syncthreads();
     if (sta)
         for (int j = tid; j < nb; j += SEL_THREADS)
-            if (sta[static_cast<size_t>(i) * nb + j]) keep[j] = 1;
+            if (sta[static_cast<size_t>(sta_row0 + i) * nb + j]) keep[j] = 1;
     __syncthreads();
     // ordered compaction (ascending block id)
-    int32_t* out = kv_index + (static_cast<size_t>(h) * nb + i) * nb;
+    int32_t* out = kv_index + (static_cast<size_t>(h) * nbq + i) * nb;
     int base = 0;
     const int lane = tid & 31, warp = tid >> 5;
     for (int j0 = 0; j0 < nb; j0 += SEL_THREADS) {
@@ -170,7 +170,7 @@ nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int n
         __syncthreads();
     }
     if (tid == 0) {
-        kv_count[static_cast<size_t>(h) * nb + i] = base;
+        kv_count[static_cast<size_t>(h) * nbq + i] = base;
         if (density_acc) {
             atomicAdd(density_acc, static_cast<float>(base));
             atomicAdd(density_acc + 1, static_cast<float>(nb));
@@ -196,21 +196,22 @@ size_t nabla_workspace_floats(int S, int heads) {
 }
 int nabla_select_launches() { return 3; }
 
-int nabla_select(const bf16* q, int ldq, const bf16* k, int ldk, int S, int heads, float P, const uint8_t* sta,
-                 int32_t* kv_count, int32_t* kv_index, float* workspace, float* density_acc, cudaStream_t st) {
-    K5_REQUIRE(S % 64 == 0 && S >= 64, "NABLA: token count must be a multiple of 64");
-    const int nb = S / 64;
-    K5_REQUIRE(nb <= NB_MAX, "NABLA: at most 2048 blocks (131072 tokens)");
+int nabla_select(const bf16* q, int ldq, int Sq, const bf16* k, int ldk, int Sk, int heads, float P, const uint8_t* sta,
+                 int sta_row0, int32_t* kv_count, int32_t* kv_index, float* workspace, float* density_acc, cudaStream_t st) {
+    K5_REQUIRE(Sq % 64 == 0 && Sq >= 64 && Sk % 64 == 0 && Sk >= 64, "NABLA: token counts must be multiples of 64");
+    const int nbq = Sq / 64, nbk = Sk / 64;
+    K5_REQUIRE(nbk <= NB_MAX, "NABLA: at most 2048 key blocks (131072 tokens)");
     K5_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0, "NABLA: pitches must be x8");
     const int cols = heads * 64;
     bf16* qa = reinterpret_cast<bf16*>(workspace);
-    bf16* ka = qa + static_cast<size_t>(nb) * cols;
-    pool64_kernel<<<nb, 256, 0, st>>>(q, ldq, cols, qa);
-    pool64_kernel<<<nb, 256, 0, st>>>(k, ldk, cols, ka);
+    bf16* ka = qa + static_cast<size_t>(nbq) * cols;
+    pool64_kernel<<<nbq, 256, 0, st>>>(q, ldq, cols, qa);
+    pool64_kernel<<<nbk, 256, 0, st>>>(k, ldk, cols, ka);
     // the reference compares against the Python double 1 - P; undo the float round trip of P first
     const double Pd = nearbyint(static_cast<double>(P) * 1e6) / 1e6;
     const float need = static_cast<float>(1.0 - Pd);
-    nabla_row_kernel<<<dim3(nb, heads), SEL_THREADS, 0, st>>>(qa, ka, nb, heads, need, sta, kv_count, kv_index, density_acc);
+    nabla_row_kernel<<<dim3(nbq, heads), SEL_THREADS, 0, st>>>(qa, ka, nbq, nbk, heads, need, sta, sta_row0, kv_count, kv_index,
+                                                               density_acc);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }

@@ -67,6 +67,36 @@ def test_sharded_forward_is_bit_identical_to_single_engine(world):
         assert torch.equal(o[f0:f0 + n], ref[f0:f0 + n]), f"rank {r} frames differ from the single-engine forward"
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_nabla_forward_is_bit_identical_to_single_engine(world):
+    """NABLA on a shard: block selection of the rank's query blocks against ALL key blocks (gathered K), STA rows of its
+    own blocks, block-sparse attention over the gathered K|V - same lists, same result as one engine."""
+    from kandinsky.models.parallelize import frame_partition
+
+    rec = torch.load(os.path.join(GOLD, "tiny_nabla_4x16x16.pt"), weights_only=False)
+    cfg = rec["cfg"]
+    T, H, W, L = rec["T"], rec["H"], rec["W"], rec["L"]
+    full, ranks = _models(cfg, T * (H // 2) * (W // 2), world)
+    img, text, pooled = _inputs(rec)
+    pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+    nb = rec["nabla"]
+    sparse = {"to_fractal": True, "P": nb["P"], "wT": nb["wT"], "wH": nb["wH"], "wW": nb["wW"], "add_sta": True}
+    ref = full(img, text, pooled, 500.0, pos, torch.arange(L), scale_factor=rec["scale_factor"], sparse_params=sparse)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in ranks]
+    outs = []
+    for m, s in zip(ranks, streams):
+        with torch.cuda.stream(s):
+            outs.append(m(img, text, pooled, 500.0, pos, torch.arange(L), scale_factor=rec["scale_factor"],
+                          sparse_params=sparse))
+    torch.cuda.synchronize()
+    dens = []
+    for r, (o, (f0, n)) in enumerate(zip(outs, frame_partition(T, world))):
+        assert torch.equal(o[f0:f0 + n], ref[f0:f0 + n]), f"rank {r} frames differ from the single-engine NABLA forward"
+        dens.append(ranks[r].last_sparse_density())
+    assert abs(sum(dens) / len(dens) - full.last_sparse_density()) < 1e-3      # equal slabs: densities average
+
+
 def test_sharded_sampler_with_cfg_matches_single_engine():
     """k5_sample on a 2-way shard (CFG: two forwards per step): each rank integrates its own frames only."""
     from kandinsky._lib import check, lib, ptr
