@@ -39,6 +39,11 @@ WORKLOADS = {
     "10s_sft_nabla": dict(T=61, H=64, W=96, L=256, Ln=64, w=5.0, sched=10.0,
                           nabla=dict(P=0.9, wT=11, wH=3, wW=3, add_sta=True), nfe=100,
                           name="config_10s_sft: 768x512x241, NABLA P=0.9 (11,3,3), 100 NFE"),
+    # the same with the adaptive part switched off (P -> 0: only the sliding-tile window survives, density 4.8 %):
+    # random weights give near-uniform attention maps (density ~0.9), trained ones sit between the two
+    "10s_sft_sta": dict(T=61, H=64, W=96, L=256, Ln=64, w=5.0, sched=10.0,
+                        nabla=dict(P=0.0, wT=11, wH=3, wW=3, add_sta=True), nfe=100,
+                        name="config_10s_sft with P=0: 768x512x241, STA window (11,3,3) only, 100 NFE"),
 }
 
 

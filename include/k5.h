@@ -99,6 +99,15 @@ int k5_engine_set_grid(k5_engine* e, int T, int H, int W, const int32_t* pos_t_h
 int k5_dit_forward(k5_engine* e, const float* x, int Cx, const void* text, int L, const int32_t* text_pos_host,
                    const void* pooled, float time, const k5_sparse* sparse, void* out, void* stream);
 
+/* MagCache variant of k5_dit_forward (kandinsky/magcache_utils.py:41-101, enabled by get_T2V_pipeline(magcache=True),
+ * kandinsky/utils.py:107-113).  slot: 0 = conditional, 1 = unconditional branch (the reference's cnt % 2).  skip == 0:
+ * run the visual blocks and cache their residual (output minus embedded input, bf16) in the slot; skip != 0: replace
+ * the visual blocks by "embedded input + cached residual".  The skip decision (accumulated magnitude-ratio error,
+ * magcache_utils.py:64-80) is host logic and lives in the Python mirror. */
+int k5_dit_forward_magcache(k5_engine* e, const float* x, int Cx, const void* text, int L, const int32_t* text_pos_host,
+                            const void* pooled, float time, const k5_sparse* sparse, void* out, int slot, int skip,
+                            void* stream);
+
 /* The whole flow-matching Euler loop on the device.  img: float32 [T,H,W,in_visual_dim], noise in / latent
  * out (updated in place).  null_text / null_pooled may be NULL when |guidance_weight - 1| <= 1e-6. */
 int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, float scheduler_scale, const void* text,

@@ -23,7 +23,7 @@ int engine_finalize(Engine* e);
 int engine_set_grid(Engine* e, int T, int H, int W, const int32_t* pt, const int32_t* ph, const int32_t* pw,
                     const float sf[3], int fractal);
 int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, const int32_t* text_pos, const bf16* pooled,
-                   float time, const k5_sparse* sp, bf16* out, cudaStream_t st);
+                   float time, const k5_sparse* sp, bf16* out, cudaStream_t st, int mag_slot, int mag_skip);
 int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, const bf16* text, int L, const bf16* pooled,
                   const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st);
 float engine_density(Engine* e);
@@ -80,7 +80,19 @@ int k5_dit_forward(k5_engine* e, const float* x, int Cx, const void* text, int L
     K5_NEED(e);
     return engine_forward(reinterpret_cast<Engine*>(e), x, Cx, static_cast<const bf16*>(text), L, text_pos_host,
                           static_cast<const bf16*>(pooled), time, sparse, static_cast<bf16*>(out),
-                          static_cast<cudaStream_t>(stream));
+                          static_cast<cudaStream_t>(stream), -1, 0);
+}
+int k5_dit_forward_magcache(k5_engine* e, const float* x, int Cx, const void* text, int L, const int32_t* text_pos_host,
+                            const void* pooled, float time, const k5_sparse* sparse, void* out, int slot, int skip,
+                            void* stream) {
+    K5_NEED(e);
+    if (slot < 0 || slot > 1) {
+        set_last_error("MagCache slot must be 0 or 1");
+        return K5_ERR_INVALID;
+    }
+    return engine_forward(reinterpret_cast<Engine*>(e), x, Cx, static_cast<const bf16*>(text), L, text_pos_host,
+                          static_cast<const bf16*>(pooled), time, sparse, static_cast<bf16*>(out),
+                          static_cast<cudaStream_t>(stream), slot, skip);
 }
 int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, float scheduler_scale, const void* text, int L,
               const void* pooled, const void* null_text, int Ln, const void* null_pooled, const k5_sparse* sparse,

@@ -101,6 +101,10 @@ struct Engine {
     float2 *rope_v = nullptr, *rope_t = nullptr, *rope_t_arange = nullptr;
     int *pos_dev = nullptr;         // [T + Hp + Wp] then text positions at +4096
     bf16 *v_c = nullptr, *v_u = nullptr;
+    // MagCache (magcache_utils.py): the embedded input of the visual stack and one cached block-stack residual per
+    // CFG branch; allocated on first use
+    bf16 *mag_x0 = nullptr, *mag_res[2] = {nullptr, nullptr};
+    bool mag_valid[2] = {false, false};
     // NABLA
     uint8_t* sta = nullptr;
     int32_t *kv_count = nullptr, *kv_index = nullptr;
@@ -736,13 +740,24 @@ int cross_attention(Engine* e, const Block& b, const bf16* text, int L, const fl
 
 }  // namespace
 
+// mag_slot < 0: plain forward.  mag_slot 0 / 1 (MagCache, conditional / unconditional branch): mag_skip == 0 runs the
+// visual blocks and stores their residual (output - embedded input) in the slot, mag_skip != 0 replaces the 32 visual
+// blocks by "embedded input + cached residual" (magcache_utils.py:64-88).
 int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, const int32_t* text_pos, const bf16* pooled,
-                   float time, const k5_sparse* sp, bf16* out, cudaStream_t st) {
+                   float time, const k5_sparse* sp, bf16* out, cudaStream_t st, int mag_slot = -1, int mag_skip = 0) {
     K5_REQUIRE(e->finalized, "forward: call k5_engine_finalize first");
     K5_REQUIRE(e->grid_set, "forward: call k5_engine_set_grid first");
     K5_REQUIRE(x && text && pooled && out, "forward: null tensor");
     K5_REQUIRE(Cx == e->Cin || Cx == e->c.in_visual_dim, "forward: x must have model-input or latent channel count");
     K5_REQUIRE(L > 0 && L <= e->c.max_text_tokens, "forward: text length out of range");
+    K5_REQUIRE(mag_slot >= -1 && mag_slot <= 1, "forward: MagCache slot must be 0 (conditional) or 1 (unconditional)");
+    if (mag_slot >= 0 && !e->mag_x0) {
+        const size_t n = static_cast<size_t>(e->c.max_tokens) * e->D;
+        K5_TRY(e->alloc(&e->mag_x0, n));
+        K5_TRY(e->alloc(&e->mag_res[0], n));
+        K5_TRY(e->alloc(&e->mag_res[1], n));
+    }
+    K5_REQUIRE(mag_slot < 0 || !mag_skip || e->mag_valid[mag_slot], "forward: MagCache skip before any residual was stored");
     K5_REQUIRE(!sp || e->fractal, "forward: NABLA needs the fractal token order (set_grid fractal=1)");
     K5_REQUIRE(!sp || (e->S % 64 == 0 && e->Sl % 64 == 0 && e->tok0 % 64 == 0),
                "forward: NABLA needs token counts (per frame, too, on a shard) divisible by 64");
@@ -800,11 +815,23 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
     }
     // --- visual transformer blocks (dit.py:61-79)
     const float2* rope_v = e->rope_v + static_cast<size_t>(e->tok0) * 32;
-    for (const Block& b : e->vblocks) {
-        const float* mod = e->modOut + b.mod_off;
-        K5_TRY(self_attention(e, b, e->x, e->xn, e->qkv, e->att, mod, S, rope_v, sp, true, st));
-        K5_TRY(cross_attention(e, b, e->te, L, mod + 3 * D, st));
-        K5_TRY(feed_forward(e, b, e->x, e->xn, e->hid, mod + 6 * D, S, st));
+    const size_t nx = static_cast<size_t>(S) * D;
+    if (mag_slot >= 0 && mag_skip) {
+        count_launch(1);
+        K5_TRY(bf16_addsub(e->x, e->mag_res[mag_slot], e->x, nx, false, st));
+    } else {
+        if (mag_slot >= 0) K5_CHECK_CUDA(cudaMemcpyAsync(e->mag_x0, e->x, nx * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+        for (const Block& b : e->vblocks) {
+            const float* mod = e->modOut + b.mod_off;
+            K5_TRY(self_attention(e, b, e->x, e->xn, e->qkv, e->att, mod, S, rope_v, sp, true, st));
+            K5_TRY(cross_attention(e, b, e->te, L, mod + 3 * D, st));
+            K5_TRY(feed_forward(e, b, e->x, e->xn, e->hid, mod + 6 * D, S, st));
+        }
+        if (mag_slot >= 0) {
+            count_launch(1);
+            K5_TRY(bf16_addsub(e->x, e->mag_x0, e->mag_res[mag_slot], nx, true, st));
+            e->mag_valid[mag_slot] = true;
+        }
     }
     // --- after_blocks / OutLayer (dit.py:150-153, nn.py:374-400): own frames of `out`
     {

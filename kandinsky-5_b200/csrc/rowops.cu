@@ -270,6 +270,23 @@ __global__ void euler_kernel(float* __restrict__ img, const bf16* __restrict__ v
     if (i < n) img[i] = __fadd_rn(img[i], bf16_round(__fmul_rn(dt, __bfloat162float(v[i]))));
 }
 
+// MagCache residual arithmetic (magcache_utils.py:82-88), bf16 tensors, 8 elements per thread:
+//   sub: out = bf16(a - b)   (residual = visual_embed_out - visual_embed_in)
+//   add: out = bf16(a + b)   (visual_embed_in + cached residual)
+__global__ void __launch_bounds__(256)
+bf16_addsub_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, size_t n8, float sign) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint4 x = a[i], y = b[i];
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o[j] = pack_bf16x2(fmaf(sign, bf16_lo(ys[j]), bf16_lo(xs[j])), fmaf(sign, bf16_hi(ys[j]), bf16_hi(xs[j])));
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 __global__ void convert_to_bf16_kernel(const void* __restrict__ src, int src_dtype, bf16* __restrict__ dst, size_t n,
                                        int rows, int cols, int ld_dst) {
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -370,6 +387,18 @@ int cfg_combine(const bf16* vc, const bf16* vu, float w, bf16* out, size_t n, cu
 
 int euler_step(float* img, const bf16* v, float dt, size_t n, cudaStream_t st) {
     euler_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(img, v, dt, n);
+    K5_CHECK_CUDA(cudaGetLastError());
+    return K5_OK;
+}
+
+int bf16_addsub(const bf16* a, const bf16* b, bf16* out, size_t n, bool subtract, cudaStream_t st) {
+    K5_REQUIRE(n % 8 == 0, "bf16_addsub: element count must be a multiple of 8");
+    if (n == 0) return K5_OK;
+    size_t blocks = (n / 8 + 255) / 256;
+    const size_t cap = static_cast<size_t>(sm_count()) * 16;
+    bf16_addsub_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(out), n / 8,
+        subtract ? -1.0f : 1.0f);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }

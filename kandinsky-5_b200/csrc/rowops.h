@@ -19,6 +19,7 @@ int rope3d_table(const float* at, const float* ah, const float* aw, int nt, int 
 int rope1d_table(const float* args, int np, const int* pos, int L, float2* table, cudaStream_t st);
 int cfg_combine(const bf16* vc, const bf16* vu, float w, bf16* out, size_t n, cudaStream_t st);
 int euler_step(float* img, const bf16* v, float dt, size_t n, cudaStream_t st);
+int bf16_addsub(const bf16* a, const bf16* b, bf16* out, size_t n, bool subtract, cudaStream_t st);
 int convert_to_bf16(const void* src, int src_dtype, bf16* dst, int rows, int cols, int ld_dst, cudaStream_t st);
 int convert_to_f32(const void* src, int src_dtype, float* dst, size_t n, bool round_bf16, cudaStream_t st);
 

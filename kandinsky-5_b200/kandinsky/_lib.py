@@ -43,6 +43,8 @@ SIGNATURES = {
                                    POINTER(c_float), c_int]),
     "k5_dit_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_int32), c_void_p, c_float,
                                POINTER(K5Sparse), c_void_p, c_void_p]),
+    "k5_dit_forward_magcache": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, POINTER(c_int32), c_void_p, c_float,
+                                        POINTER(K5Sparse), c_void_p, c_int, c_int, c_void_p]),
     "k5_sample": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int,
                           c_void_p, POINTER(K5Sparse), c_void_p]),
     "k5_engine_attention_timing": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),

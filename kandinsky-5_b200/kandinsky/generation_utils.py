@@ -84,7 +84,7 @@ def generate(model, device, shape, num_steps, text_embeds, null_text_embeds, vis
     scale_factor = _get(conf, "metrics.scale_factor")
     arange_pos = (list(text_rope_pos.tolist()) == list(range(len(text_rope_pos)))
                   and list(null_text_rope_pos.tolist()) == list(range(len(null_text_rope_pos))))
-    if hasattr(model, "_engine") and arange_pos:
+    if hasattr(model, "_engine") and arange_pos and getattr(model, "_magcache", None) is None:
         # whole loop on the device
         T, H, W, _ = img.shape
         fractal = bool(sparse_params["to_fractal"]) if sparse_params is not None else False

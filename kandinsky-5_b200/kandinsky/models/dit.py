@@ -88,6 +88,7 @@ class DiffusionTransformer3D(nn.Module):
         self._grid_key = None
         self._pending = None          # CPU state dict kept until .to(cuda) creates the engine
         self.dist_rank, self.dist_world = 0, 1
+        self._magcache = None         # magcache_utils.MagCacheState when get_T2V_pipeline(magcache=True)
 
     # ---- engine lifetime -------------------------------------------------------------------------------
     def _create_engine(self, device):
@@ -246,9 +247,16 @@ class DiffusionTransformer3D(nn.Module):
             tpos_arr = None if tpos == list(range(L)) else (c_int32 * L)(*tpos)
             out = torch.empty(T, H, W, self.cfg["out_visual_dim"], device=self._device, dtype=torch.bfloat16)
             sp = self._sparse_struct(sparse_params)
-            check(lib().k5_dit_forward(self._engine, ptr(x), C, ptr(text), L, tpos_arr, ptr(pooled),
-                                       float(time.reshape(-1)[0].item()) if torch.is_tensor(time) else float(time),
-                                       ctypes.byref(sp) if sp is not None else None, ptr(out), stream_ptr()))
+            t = float(time.reshape(-1)[0].item()) if torch.is_tensor(time) else float(time)
+            spp = ctypes.byref(sp) if sp is not None else None
+            if self._magcache is None:
+                check(lib().k5_dit_forward(self._engine, ptr(x), C, ptr(text), L, tpos_arr, ptr(pooled), t, spp, ptr(out),
+                                           stream_ptr()))
+            else:
+                slot, skip = self._magcache.next()
+                check(lib().k5_dit_forward_magcache(self._engine, ptr(x), C, ptr(text), L, tpos_arr, ptr(pooled), t, spp,
+                                                    ptr(out), slot, 1 if skip else 0, stream_ptr()))
+                self.last_magcache_decision = (slot, skip)
         return out
 
     __call__ = forward

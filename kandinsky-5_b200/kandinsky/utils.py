@@ -69,8 +69,6 @@ def get_T2V_pipeline(device_map: Union[str, torch.device, dict], resolution: int
     `max_tokens`) let callers inject side models / weights; the reference's Hugging Face downloads are out of
     scope (no network) — missing checkpoints raise FileNotFoundError instead."""
     assert resolution in [512]
-    if magcache:
-        raise NotImplementedError("MagCache is not part of this engine yet (SURVEY.md §8f rank 1)")
     if offload:
         raise NotImplementedError("offload moves the reference's torch modules between CPU and GPU; the engine keeps "
                                   "its repacked weights resident in HBM")
@@ -100,6 +98,11 @@ def get_T2V_pipeline(device_map: Union[str, torch.device, dict], resolution: int
         from safetensors.torch import load_file
 
         state_dict = load_file(path)
+    if magcache:
+        # kandinsky/utils.py:107-113
+        from .magcache_utils import set_magcache_params
+
+        set_magcache_params(dit, conf.magcache.mag_ratios, conf.model.num_steps, conf.model.guidance_weight == 1.0)
     dit.load_state_dict(state_dict, assign=True)
     dit = dit.to(device_map["dit"])
     if world_size > 1:

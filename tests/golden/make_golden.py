@@ -244,6 +244,59 @@ def run_sampler_case(mods, name, cfg, T, H, W, L, Ln, steps, w, sched):
     print(name, tuple(out.shape), out.dtype, float(out.abs().mean()))
 
 
+def run_magcache_case(mods, name, cfg, T, H, W, L, Ln, steps, w, sched, mag_ratios):
+    """generate() with the reference's MagCache forward (kandinsky/magcache_utils.py) swapped in; records which forwards
+    skipped the visual blocks (number of visual-block executions per forward) and the final latent."""
+    from oracle import dit_oracle as O
+
+    mc = importlib.import_module("kandinsky.magcache_utils")
+    sd = O.synthetic_state_dict(cfg, seed=0)
+    model = build_ref_model(mods, cfg, sd)
+    cls = model.__class__
+    plain_forward = cls.forward
+    mc.set_magcache_params(model, list(mag_ratios), steps, abs(w - 1.0) < 1e-6)
+    img, text, pooled = synth_inputs(T, H, W, L)
+    _, ntext, npooled = synth_inputs(T, H, W, Ln, seed=2)
+    pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+    conf = Conf({"metrics": {"scale_factor": (1.0, 2.0, 2.0)},
+                 "model": {"dit_params": dict(cfg), "attention": {"type": "flash"}}})
+    gu = mods["generation_utils"]
+    calls = []
+    blk = model.visual_transformer_blocks[0]
+    real_blk_forward = blk.forward
+
+    def counting(*a, **k):
+        calls[-1] += 1
+        return real_blk_forward(*a, **k)
+
+    blk.forward = counting
+    mag_forward = cls.forward
+
+    def recording_forward(self, *a, **k):
+        calls.append(0)
+        return mag_forward(self, *a, **k)
+
+    cls.forward = recording_forward
+    real_randn, real_gen = torch.randn, torch.Generator
+    torch.randn = lambda *a, **k: img.clone()
+    torch.Generator = lambda device=None: real_gen()
+    gu.tqdm = lambda it, **k: it
+    try:
+        with torch.no_grad(), AutocastEmu(), EmuAutocast("cuda", dtype=torch.bfloat16):
+            out = gu.generate(model, "cpu", (T, H, W, 16), steps,
+                              {"text_embeds": text, "pooled_embed": pooled},
+                              {"text_embeds": ntext, "pooled_embed": npooled},
+                              pos, torch.arange(L), torch.arange(Ln), w, sched, conf, seed=6554)
+    finally:
+        torch.randn, torch.Generator = real_randn, real_gen
+        cls.forward = plain_forward
+    skipped = [c == 0 for c in calls]
+    rec = dict(name=name, cfg=cfg, T=T, H=H, W=W, L=L, Ln=Ln, steps=steps, guidance_weight=w, scheduler_scale=sched,
+               mag_ratios=list(mag_ratios), skipped=skipped, out=out.clone(), scale_factor=(1.0, 2.0, 2.0), weight_seed=0)
+    torch.save(rec, os.path.join(HERE, name + ".pt"))
+    print(name, tuple(out.shape), "forwards", len(calls), "skipped", sum(skipped), float(out.abs().mean()))
+
+
 def main():
     mods = import_reference()
     torch.manual_seed(0)
@@ -256,6 +309,11 @@ def main():
                      nabla=dict(P=0.6, wT=3, wH=3, wW=3))
     # whole sampler with CFG (two forwards / step), 4 Euler steps
     run_sampler_case(mods, "tiny_sampler_cfg", TINY, 2, 16, 16, 24, 9, steps=4, w=5.0, sched=5.0)
+    # MagCache: 10 CFG steps = 20 forwards, calibration curve shaped like configs/config_5s_sft.yaml's (some steps skip)
+    ratios = [0.92, 0.915, 0.95, 0.953, 1.05, 1.049, 1.03, 1.031, 1.02, 1.021, 1.02, 1.019, 1.015, 1.016, 1.01, 1.011,
+              0.99, 0.989, 0.94, 0.937]
+    run_magcache_case(mods, "tiny_sampler_magcache", TINY, 2, 16, 16, 24, 9, steps=10, w=5.0, sched=5.0,
+                      mag_ratios=ratios[:18])
 
 
 if __name__ == "__main__":

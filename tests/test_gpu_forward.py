@@ -128,3 +128,46 @@ def test_nabla_forward_matches_reference_golden():
     print(f"nabla: engine-vs-reference {err:.2e}  density {dens:.4f} (reference {ref_dens:.4f})")
     assert err < 1.5e-2
     assert abs(dens - ref_dens) < 0.01
+
+
+def test_magcache_sampler_matches_reference_golden():
+    """MagCache (kandinsky/magcache_utils.py): the skip decisions of the mirror's state machine equal the reference's,
+    and the latent after 10 CFG steps (12 of 20 forwards served from the residual cache) matches its output."""
+    from kandinsky.generation_utils import generate
+    from kandinsky.magcache_utils import set_magcache_params
+
+    rec = torch.load(os.path.join(GOLD, "tiny_sampler_magcache.pt"), weights_only=False)
+    cfg = rec["cfg"]
+    T, H, W, L, Ln = rec["T"], rec["H"], rec["W"], rec["L"], rec["Ln"]
+    model, _ = build_model(cfg, T * (H // 2) * (W // 2))
+    set_magcache_params(model, rec["mag_ratios"], rec["steps"], False)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(T, H, W, 16, generator=g)
+    text = torch.randn(L, 3584, generator=g).to(torch.bfloat16)
+    pooled = torch.randn(1, 768, generator=g).to(torch.bfloat16)
+    g2 = torch.Generator().manual_seed(2)
+    torch.randn(T, H, W, 16, generator=g2)
+    ntext = torch.randn(Ln, 3584, generator=g2).to(torch.bfloat16)
+    npooled = torch.randn(1, 768, generator=g2).to(torch.bfloat16)
+    pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+    conf = {"metrics": {"scale_factor": rec["scale_factor"]},
+            "model": {"dit_params": dict(cfg), "attention": {"type": "flash"}}}
+    te = {"text_embeds": text.cuda(), "pooled_embed": pooled.cuda()}
+    nte = {"text_embeds": ntext.cuda(), "pooled_embed": npooled.cuda()}
+    decisions = []
+    real_next = model._magcache.next
+
+    def spy():
+        d = real_next()
+        decisions.append(d)
+        return d
+
+    model._magcache.next = spy
+    out = generate(model, "cuda", (T, H, W, 16), rec["steps"], te, nte, pos, torch.arange(L), torch.arange(Ln),
+                   rec["guidance_weight"], rec["scheduler_scale"], conf, noise=img)
+    assert [s for _, s in decisions] == rec["skipped"]                 # host logic: bit-exact
+    assert [s for s, _ in decisions] == [i % 2 for i in range(len(decisions))]
+    err = rel_l2(out, rec["out"])
+    print(f"magcache sampler: engine-vs-reference {err:.2e}, {sum(rec['skipped'])} of {len(decisions)} forwards skipped")
+    assert err < 2e-2
+    assert model._magcache.cnt == 0                                    # the schedule wrapped: ready for the next sample
