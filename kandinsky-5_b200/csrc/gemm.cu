@@ -26,6 +26,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int GEMM_THREADS = 384;     // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue, two per TMEM lane quarter
 
 template <int BN>
 struct GemmCfg {
@@ -34,14 +35,14 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int XPOSE_BYTES = 4 * 32 * 128;   // per epilogue warp: 32 rows x 128 B, for the peer scatter
+    static constexpr int XPOSE_BYTES = 8 * 32 * 128;   // per epilogue warp: 32 rows x 128 B, for the peer scatter
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XPOSE_BYTES;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue e) {
     using Cfg = GemmCfg<BN>;
@@ -73,7 +74,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 128);
+            mbar_init(&tempty[s], 256);
         }
         fence_barrier_init();
     }
@@ -138,8 +139,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (4 warps, thread = output row) =====================
+        // ===================== epilogue (8 warps, thread = output row x half of the tile's columns) =====================
+        // A warp may only touch TMEM lanes 32 * (warp % 4) .. +31, so warps 4-7 and 8-11 both cover the 128 rows; the
+        // first set takes the lower half of the BN columns, the second the upper half.
         const int wq = warp & 3;
+        const int chalf = (warp - 4) >> 2;
         const int lane = threadIdx.x & 31;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -155,7 +159,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
             if constexpr (EPI == EPI_HEADS) {
                 // one head (64 columns) at a time
-                for (int c = 0; c < BN / 64; ++c) {
+                constexpr int HPW = (BN / 64 + 1) / 2;          // heads per warp set
+                for (int c = chalf * HPW; c < BN / 64 && c < (chalf + 1) * HPW; ++c) {
                     uint32_t raw[64];
                     tmem_ld32(t_row + c * 64, raw);
                     tmem_ld32(t_row + c * 64 + 32, raw + 32);
@@ -164,25 +169,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float x[64];
                     float ss = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) {
-                        float b = e.bias ? __ldg(e.bias + col0 + i) : 0.f;
-                        x[i] = bf16_round(__uint_as_float(raw[i]) + b);
-                        ss += x[i] * x[i];
+                    for (int i = 0; i < 16; ++i) {
+                        // bias / norm weights / rope are read 16 bytes at a time (all pointers are 16-byte aligned:
+                        // col0 is a multiple of 64, the rope row is 256 bytes)
+                        const float4 b = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                        x[4 * i + 0] = bf16_round(__uint_as_float(raw[4 * i + 0]) + b.x);
+                        x[4 * i + 1] = bf16_round(__uint_as_float(raw[4 * i + 1]) + b.y);
+                        x[4 * i + 2] = bf16_round(__uint_as_float(raw[4 * i + 2]) + b.z);
+                        x[4 * i + 3] = bf16_round(__uint_as_float(raw[4 * i + 3]) + b.w);
+                        ss += x[4 * i] * x[4 * i] + x[4 * i + 1] * x[4 * i + 1] + x[4 * i + 2] * x[4 * i + 2] +
+                              x[4 * i + 3] * x[4 * i + 3];
                     }
                     if (col0 < e.norm_cols) {
-                        const float* w = (col0 < e.norm_split) ? e.norm_w0 : e.norm_w1;
+                        const float4* w4 = reinterpret_cast<const float4*>((col0 < e.norm_split) ? e.norm_w0 : e.norm_w1);
                         const float inv = rsqrtf(ss * (1.0f / 64.0f) + 1.1920928955078125e-07f);
 #pragma unroll
-                        for (int i = 0; i < 64; ++i) x[i] = bf16_round(x[i] * inv * __ldg(w + i));
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 w = __ldg(w4 + i);
+                            x[4 * i + 0] = bf16_round(x[4 * i + 0] * inv * w.x);
+                            x[4 * i + 1] = bf16_round(x[4 * i + 1] * inv * w.y);
+                            x[4 * i + 2] = bf16_round(x[4 * i + 2] * inv * w.z);
+                            x[4 * i + 3] = bf16_round(x[4 * i + 3] * inv * w.w);
+                        }
                         if (col0 < e.rope_cols && row_ok) {
-                            const float2* rp = e.rope + static_cast<size_t>(row) * 32;
+                            const float4* rp = reinterpret_cast<const float4*>(e.rope + static_cast<size_t>(row) * 32);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float2 cs = __ldg(rp + i);
-                                const float a = x[2 * i], b2 = x[2 * i + 1];
+                            for (int i = 0; i < 16; ++i) {
+                                const float4 cs = __ldg(rp + i);        // (cos, sin) of pairs 2i and 2i + 1
+                                const float a0 = x[4 * i], b0 = x[4 * i + 1], a1 = x[4 * i + 2], b1 = x[4 * i + 3];
                                 // reference: (rope * x_).sum(-1): products rounded separately, then added
-                                x[2 * i] = bf16_round(__fadd_rn(__fmul_rn(cs.x, a), __fmul_rn(-cs.y, b2)));
-                                x[2 * i + 1] = bf16_round(__fadd_rn(__fmul_rn(cs.y, a), __fmul_rn(cs.x, b2)));
+                                x[4 * i + 0] = bf16_round(__fadd_rn(__fmul_rn(cs.x, a0), __fmul_rn(-cs.y, b0)));
+                                x[4 * i + 1] = bf16_round(__fadd_rn(__fmul_rn(cs.y, a0), __fmul_rn(cs.x, b0)));
+                                x[4 * i + 2] = bf16_round(__fadd_rn(__fmul_rn(cs.z, a1), __fmul_rn(-cs.w, b1)));
+                                x[4 * i + 3] = bf16_round(__fadd_rn(__fmul_rn(cs.w, a1), __fmul_rn(cs.z, b1)));
                             }
                         }
                     }
@@ -190,7 +210,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         // K | V columns of a temporal shard: all-gather fused into the epilogue.  Transpose the
                         // warp's 32 x 128 B through shared memory (XOR-swizzled 16-byte chunks, conflict free) so
                         // that 8 lanes cover one 128-byte line, then store the lines to every rank's K|V buffer.
-                        uint4* xw = reinterpret_cast<uint4*>(xpose + wq * 4096);
+                        uint4* xw = reinterpret_cast<uint4*>(xpose + (warp - 4) * 4096);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             uint4 v;
@@ -233,7 +253,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             } else {
-                for (int c = 0; c < BN / 32; ++c) {
+                constexpr int CPW = (BN / 32 + 1) / 2;          // 32-column chunks per warp set
+                for (int c = chalf * CPW; c < BN / 32 && c < (chalf + 1) * CPW; ++c) {
                     uint32_t raw[32];
                     tmem_ld32(t_row + c * 32, raw);
                     tmem_wait_ld();
@@ -247,11 +268,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int i = 0; i < 4; ++i) {
                             float y[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int cc = 8 * i + j;
-                                float v = __uint_as_float(raw[cc]);
-                                if (e.bias) v += __ldg(e.bias + col0 + cc);
-                                y[j] = v;
+                            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(raw[8 * i + j]);
+                            if (e.bias) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + 2 * i);
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + 2 * i + 1);
+                                y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+                                y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
                             }
                             if constexpr (EPI == EPI_GELU) {
 #pragma unroll
@@ -260,12 +282,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if constexpr (EPI == EPI_GATE) {
                                 const uint4 r = res[i];
                                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.gate + col0) + 2 * i);
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.gate + col0) + 2 * i + 1);
+                                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const float g0 = __ldg(e.gate + col0 + 8 * i + 2 * j);
-                                    const float g1 = __ldg(e.gate + col0 + 8 * i + 2 * j + 1);
-                                    y[2 * j] = __fadd_rn(bf16_lo(rr[j]), __fmul_rn(g0, bf16_round(y[2 * j])));
-                                    y[2 * j + 1] = __fadd_rn(bf16_hi(rr[j]), __fmul_rn(g1, bf16_round(y[2 * j + 1])));
+                                    y[2 * j] = __fadd_rn(bf16_lo(rr[j]), __fmul_rn(gg[2 * j], bf16_round(y[2 * j])));
+                                    y[2 * j + 1] = __fadd_rn(bf16_hi(rr[j]), __fmul_rn(gg[2 * j + 1], bf16_round(y[2 * j + 1])));
                                 }
                             }
                             uint4 o;
@@ -302,7 +325,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, 
     }
     const int tiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, e);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, e);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }
@@ -329,6 +352,9 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
     K5_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "GEMM: K / pitches must be multiples of 8 elements");
     K5_REQUIRE(e.out != nullptr && e.ldo % 8 == 0, "GEMM: output pitch must be a multiple of 8 elements");
     if (epi == EPI_GATE) K5_REQUIRE(e.resid && e.gate && e.ldr % 8 == 0, "GEMM: gate epilogue needs resid/gate");
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    K5_REQUIRE(al16(e.bias) && al16(e.gate) && al16(e.norm_w0) && al16(e.norm_w1) && al16(e.rope),
+               "GEMM: bias / gate / norm weights / rope must be 16-byte aligned");
     if (epi == EPI_HEADS) {
         K5_REQUIRE(e.norm_cols % 64 == 0 && e.norm_split % 64 == 0 && e.rope_cols % 64 == 0, "GEMM: head split must be x64");
         K5_REQUIRE(e.norm_cols == 0 || (e.norm_w0 && e.norm_w1), "GEMM: head epilogue needs norm weights");
