@@ -22,15 +22,20 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 
-template <int BN>
+// MT = M tiles (128 positions each) that share one weight tile: with 128 output channels a 128 x 128 tile pulls
+// 128 B / clk / SM of operands out of L2 (measured 594 TFLOP/s); two position tiles per weight tile cut the
+// weight traffic and the TMA requests per FLOP to the level of the 128 x 256 tile.
+template <int BN, int MT>
 struct ConvCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 8 ? (200 * 1024 / STAGE_BYTES) : 8;
+    static constexpr int TMEM_COLS = 2 * MT * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(TMEM_COLS <= 512, "accumulators must fit TMEM");
 };
+constexpr int CONV_THREADS = 384;      // warps 0-2: TMA / MMA / TMEM alloc; warps 4-7, 8-11: epilogue of M tile 0, 1
 
 struct ConvParams {
     int T, H, W, Cin, Cout;
@@ -52,10 +57,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int MT>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvParams p) {
-    using Cfg = ConvCfg<BN>;
+    using Cfg = ConvCfg<BN, MT>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -70,7 +75,8 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int n_tiles_n = (p.Cout + BN - 1) / BN;
     const int tiles_per_frame = p.tiles_w * p.tiles_h;
     const int n_tiles_m = ((p.T + p.bt - 1) / p.bt) * tiles_per_frame;
-    const int num_tiles = n_tiles_m * n_tiles_n;
+    const int n_groups_m = (n_tiles_m + MT - 1) / MT;         // groups of MT consecutive position tiles
+    const int num_tiles = n_groups_m * n_tiles_n;
     const int cblocks = p.Cin / BK;
     const int nkb = 27 * cblocks;
 
@@ -85,7 +91,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 128);
+            mbar_init(&tempty[s], 128 * MT);
         }
         fence_barrier_init();
     }
@@ -101,12 +107,17 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles_n;
+                const int mg = tile / n_tiles_n;
                 const int n0 = (tile % n_tiles_n) * BN;
-                const int t = (mt / tiles_per_frame) * p.bt;
-                const int r = mt % tiles_per_frame;
-                const int h0 = (r / p.tiles_w) * p.bh;
-                const int w0 = (r % p.tiles_w) * p.bw;
+                int t[MT], h0[MT], w0[MT];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const int mt = mg * MT + m;                   // may run past the volume: TMA zero-fills, epilogue skips
+                    const int r = mt % tiles_per_frame;
+                    t[m] = (mt / tiles_per_frame) * p.bt;
+                    h0[m] = (r / p.tiles_w) * p.bh;
+                    w0[m] = (r % p.tiles_w) * p.bw;
+                }
                 int kb = 0;
                 for (int tap = 0; tap < 27; ++tap) {
                     const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
@@ -115,8 +126,10 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                         // padded coordinates: output (t, h, w), tap (kt, kh, kw) reads xpad[t + kt, h + kh, w + kw]
-                        tma_load_4d(sa, &tmX, &full[stage], cb * BK, w0 + kw, h0 + kh, t + kt);
-                        tma_load_2d(sa + Cfg::A_BYTES, &tmW, &full[stage], kb * BK, n0);
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+                            tma_load_4d(sa + m * Cfg::A_BYTES, &tmX, &full[stage], cb * BK, w0[m] + kw, h0[m] + kh, t[m] + kt);
+                        tma_load_2d(sa + MT * Cfg::A_BYTES, &tmW, &full[stage], kb * BK, n0);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -137,16 +150,20 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * MT * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint32_t sb = sa + MT * Cfg::A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_ss(d_tmem, umma_desc_sw128(sa + k * 32, 0, 1024), umma_desc_sw128(sb + k * 32, 0, 1024), idesc,
-                                (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t bd = umma_desc_sw128(sb + k * 32, 0, 1024);
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+                            umma_ss(d_tmem + m * BN, umma_desc_sw128(sa + m * Cfg::A_BYTES + k * 32, 0, 1024), bd, idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit(&empty[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
@@ -156,26 +173,27 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 umma_commit(&tfull[acc]);
             }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue (4 warps, thread = output position) =====================
+    } else if (warp >= 4 && warp < 4 + 4 * MT) {
+        // ===================== epilogue (4 warps per M tile, thread = output position) =====================
         const int wq = warp & 3;
+        const int msel = (warp - 4) >> 2;                         // which of the MT position tiles
         const int lane = threadIdx.x & 31;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int mt = tile / n_tiles_n;
+            const int mt = (tile / n_tiles_n) * MT + msel;
             const int n0 = (tile % n_tiles_n) * BN;
             const int r = mt % tiles_per_frame;
             const int row = wq * 32 + lane;                       // row of the tile = (tl * bh + hl) * bw + wl
             const int t = (mt / tiles_per_frame) * p.bt + row / (p.bw * p.bh);
             const int h = (r / p.tiles_w) * p.bh + (row / p.bw) % p.bh;
             const int w = (r % p.tiles_w) * p.bw + row % p.bw;
-            const bool row_ok = t < p.T;
+            const bool row_ok = t < p.T && mt < n_tiles_m;
             const size_t pos = (static_cast<size_t>(row_ok ? t : 0) * p.H + h) * p.W + w;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(wq * 32) << 16);
+            const uint32_t t_row = tmem_base + (acc * MT + msel) * BN + (static_cast<uint32_t>(wq * 32) << 16);
             for (int c = 0; c < BN / 32; ++c) {
                 const int col0 = n0 + c * 32;
                 if (col0 >= p.Cout) break;                        // warp-uniform
@@ -190,14 +208,18 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float y[8];
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + 2 * i);
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + 2 * i + 1);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            y[j] = bf16_round(__uint_as_float(raw[8 * i + j]) + __ldg(p.bias + col0 + 8 * i + j));
+                        for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(raw[8 * i + j]) + bb[j];
                         if (res) {
+                            // conv output is a bf16 tensor before the residual add (vae.py:274): round, then add
                             const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * i);
                             const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
+                                bf16_round2(y[2 * j], y[2 * j + 1]);
                                 y[2 * j] = __fadd_rn(y[2 * j], bf16_lo(rr[j]));
                                 y[2 * j + 1] = __fadd_rn(y[2 * j + 1], bf16_hi(rr[j]));
                             }
@@ -266,18 +288,19 @@ int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t C, uint64_t Wp, ui
     return K5_OK;
 }
 
-template <int BN>
+template <int BN, int MT>
 int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t st) {
-    using Cfg = ConvCfg<BN>;
+    using Cfg = ConvCfg<BN, MT>;
     static bool configured = false;
-    auto kern = conv3d_kernel<BN>;
+    auto kern = conv3d_kernel<BN, MT>;
     if (!configured) {
         K5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    const int tiles = ((p.T + p.bt - 1) / p.bt) * p.tiles_w * p.tiles_h * ((p.Cout + BN - 1) / BN);
+    const int mtiles = ((p.T + p.bt - 1) / p.bt) * p.tiles_w * p.tiles_h;
+    const int tiles = ((mtiles + MT - 1) / MT) * ((p.Cout + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmX, tmW, p);
+    kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(tmX, tmW, p);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }
@@ -316,9 +339,9 @@ int conv3d_causal(const bf16* xpad, int T, int H, int W, int Cin, const bf16* w,
     K5_TRY(make_tmap_4d(&tmX, xpad, Cin, W + 2, H + 2, T + 2, bw, bh, bt));
     const int BN = (Cout_pad % 256 == 0) ? 256 : (Cout_pad % 128 == 0 ? 128 : 64);
     K5_TRY(make_tmap_2d_bf16(&tmW, w, Cout_pad, static_cast<uint64_t>(27) * Cin, static_cast<uint64_t>(27) * Cin, BN));
-    if (BN == 256) return launch_conv<256>(tmX, tmW, p, st);
-    if (BN == 128) return launch_conv<128>(tmX, tmW, p, st);
-    return launch_conv<64>(tmX, tmW, p, st);
+    if (BN == 256) return launch_conv<256, 1>(tmX, tmW, p, st);
+    if (BN == 128) return launch_conv<128, 2>(tmX, tmW, p, st);
+    return launch_conv<64, 2>(tmX, tmW, p, st);
 }
 
 }  // namespace k5

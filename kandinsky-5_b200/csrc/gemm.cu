@@ -153,6 +153,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int n0 = (tile % n_tiles_n) * BN;
             const int row = m0 + wq * 32 + lane;
             const bool row_ok = row < M;
+            // RoPE angles depend on the row only: fetch this row's 32 (cos, sin) pairs once per tile, BEFORE waiting for
+            // the accumulator, so that the L2 round trip hides behind the main loop instead of stalling every head.
+            float4 rope_row[16];
+            bool has_rope = false;
+            if constexpr (EPI == EPI_HEADS) {
+                has_rope = row_ok && n0 < e.rope_cols;
+                if (has_rope) {
+                    const float4* rp = reinterpret_cast<const float4*>(e.rope + static_cast<size_t>(row) * 32);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) rope_row[i] = __ldg(rp + i);
+                }
+            }
+            // Gated residual: this thread's slice of the residual row (HBM, not L2 resident) is fetched before the wait too.
+            constexpr int CPW_ = (BN / 32 + 1) / 2;
+            uint4 resid_row[EPI == EPI_GATE ? 4 * CPW_ : 1];
+            if constexpr (EPI == EPI_GATE) {
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < CPW_; ++c) {
+                        const int cc = chalf * CPW_ + c;
+                        if (cc < BN / 32) {
+                            const uint4* res = reinterpret_cast<const uint4*>(e.resid + static_cast<size_t>(row) * e.ldr + n0 + cc * 32);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) resid_row[4 * c + i] = res[i];
+                        }
+                    }
+                }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(wq * 32) << 16);
@@ -174,35 +202,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         // col0 is a multiple of 64, the rope row is 256 bytes)
                         const float4 b = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i)
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                        x[4 * i + 0] = bf16_round(__uint_as_float(raw[4 * i + 0]) + b.x);
-                        x[4 * i + 1] = bf16_round(__uint_as_float(raw[4 * i + 1]) + b.y);
-                        x[4 * i + 2] = bf16_round(__uint_as_float(raw[4 * i + 2]) + b.z);
-                        x[4 * i + 3] = bf16_round(__uint_as_float(raw[4 * i + 3]) + b.w);
-                        ss += x[4 * i] * x[4 * i] + x[4 * i + 1] * x[4 * i + 1] + x[4 * i + 2] * x[4 * i + 2] +
-                              x[4 * i + 3] * x[4 * i + 3];
+                        x[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x;
+                        x[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
+                        x[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
+                        x[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
                     }
-                    if (col0 < e.norm_cols) {
+                    // Rounding points of the reference (bf16 Linear output; bf16 after RMSNorm; bf16 after RoPE) are kept,
+                    // but a value that is only rounded to be packed right away is rounded once, by the pack itself.
+                    const bool normed = col0 < e.norm_cols;
+                    if (normed) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            bf16_round2(x[2 * i], x[2 * i + 1]);
+                            ss = fmaf(x[2 * i], x[2 * i], ss);
+                            ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
+                        }
                         const float4* w4 = reinterpret_cast<const float4*>((col0 < e.norm_split) ? e.norm_w0 : e.norm_w1);
                         const float inv = rsqrtf(ss * (1.0f / 64.0f) + 1.1920928955078125e-07f);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float4 w = __ldg(w4 + i);
-                            x[4 * i + 0] = bf16_round(x[4 * i + 0] * inv * w.x);
-                            x[4 * i + 1] = bf16_round(x[4 * i + 1] * inv * w.y);
-                            x[4 * i + 2] = bf16_round(x[4 * i + 2] * inv * w.z);
-                            x[4 * i + 3] = bf16_round(x[4 * i + 3] * inv * w.w);
+                            x[4 * i + 0] = x[4 * i + 0] * inv * w.x;
+                            x[4 * i + 1] = x[4 * i + 1] * inv * w.y;
+                            x[4 * i + 2] = x[4 * i + 2] * inv * w.z;
+                            x[4 * i + 3] = x[4 * i + 3] * inv * w.w;
                         }
-                        if (col0 < e.rope_cols && row_ok) {
-                            const float4* rp = reinterpret_cast<const float4*>(e.rope + static_cast<size_t>(row) * 32);
+                        if (col0 < e.rope_cols && has_rope) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float4 cs = __ldg(rp + i);        // (cos, sin) of pairs 2i and 2i + 1
+                                const float4 cs = rope_row[i];          // (cos, sin) of pairs 2i and 2i + 1
+                                bf16_round2(x[4 * i], x[4 * i + 1]);
+                                bf16_round2(x[4 * i + 2], x[4 * i + 3]);
                                 const float a0 = x[4 * i], b0 = x[4 * i + 1], a1 = x[4 * i + 2], b1 = x[4 * i + 3];
                                 // reference: (rope * x_).sum(-1): products rounded separately, then added
-                                x[4 * i + 0] = bf16_round(__fadd_rn(__fmul_rn(cs.x, a0), __fmul_rn(-cs.y, b0)));
-                                x[4 * i + 1] = bf16_round(__fadd_rn(__fmul_rn(cs.y, a0), __fmul_rn(cs.x, b0)));
-                                x[4 * i + 2] = bf16_round(__fadd_rn(__fmul_rn(cs.z, a1), __fmul_rn(-cs.w, b1)));
-                                x[4 * i + 3] = bf16_round(__fadd_rn(__fmul_rn(cs.w, a1), __fmul_rn(cs.z, b1)));
+                                x[4 * i + 0] = __fadd_rn(__fmul_rn(cs.x, a0), __fmul_rn(-cs.y, b0));
+                                x[4 * i + 1] = __fadd_rn(__fmul_rn(cs.y, a0), __fmul_rn(cs.x, b0));
+                                x[4 * i + 2] = __fadd_rn(__fmul_rn(cs.z, a1), __fmul_rn(-cs.w, b1));
+                                x[4 * i + 3] = __fadd_rn(__fmul_rn(cs.w, a1), __fmul_rn(cs.z, b1));
                             }
                         }
                     }
@@ -254,16 +290,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             } else {
                 constexpr int CPW = (BN / 32 + 1) / 2;          // 32-column chunks per warp set
-                for (int c = chalf * CPW; c < BN / 32 && c < (chalf + 1) * CPW; ++c) {
+#pragma unroll
+                for (int cl = 0; cl < CPW; ++cl) {
+                    const int c = chalf * CPW + cl;
+                    if (c >= BN / 32) break;
                     uint32_t raw[32];
                     tmem_ld32(t_row + c * 32, raw);
                     tmem_wait_ld();
                     const int col0 = n0 + c * 32;
                     if (row_ok) {
                         uint4* dst = reinterpret_cast<uint4*>(e.out + static_cast<size_t>(row) * e.ldo + col0);
-                        const uint4* res = nullptr;
-                        if constexpr (EPI == EPI_GATE)
-                            res = reinterpret_cast<const uint4*>(e.resid + static_cast<size_t>(row) * e.ldr + col0);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             float y[8];
@@ -277,18 +313,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                             if constexpr (EPI == EPI_GELU) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) y[j] = gelu_erf(bf16_round(y[j]));
+                                for (int j = 0; j < 4; ++j) {
+                                    bf16_round2(y[2 * j], y[2 * j + 1]);
+                                    y[2 * j] = gelu_erf(y[2 * j]);
+                                    y[2 * j + 1] = gelu_erf(y[2 * j + 1]);
+                                }
                             }
                             if constexpr (EPI == EPI_GATE) {
-                                const uint4 r = res[i];
+                                const uint4 r = resid_row[4 * cl + i];
                                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
                                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.gate + col0) + 2 * i);
                                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.gate + col0) + 2 * i + 1);
                                 const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    y[2 * j] = __fadd_rn(bf16_lo(rr[j]), __fmul_rn(gg[2 * j], bf16_round(y[2 * j])));
-                                    y[2 * j + 1] = __fadd_rn(bf16_hi(rr[j]), __fmul_rn(gg[2 * j + 1], bf16_round(y[2 * j + 1])));
+                                    bf16_round2(y[2 * j], y[2 * j + 1]);
+                                    y[2 * j] = __fadd_rn(bf16_lo(rr[j]), __fmul_rn(gg[2 * j], y[2 * j]));
+                                    y[2 * j + 1] = __fadd_rn(bf16_hi(rr[j]), __fmul_rn(gg[2 * j + 1], y[2 * j + 1]));
                                 }
                             }
                             uint4 o;

@@ -188,6 +188,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// Round two values to bf16 and back with ONE packed conversion (F2FP, ALU pipe) + two bit operations; the scalar
+// cvt.rn.bf16.f32 is an F2F on the quarter-rate conversion pipe.
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+    uint32_t u;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+    a = __uint_as_float(u << 16);
+    b = __uint_as_float(u & 0xFFFF0000u);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 __device__ __forceinline__ float fast_exp2(float x) {
