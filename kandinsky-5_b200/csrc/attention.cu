@@ -129,7 +129,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     const int h = item / n_qpairs;
                     const int q0 = (item % n_qpairs) * 2 * QT;
                     for (int a = 0; a < 2; ++a) {
-                        mbar_wait(&B->q_empty[a], (i & 1) ^ 1);
+                        mbar_wait_parked(&B->q_empty[a], (i & 1) ^ 1);
                         mbar_expect_tx(&B->q_full[a], TILE_BYTES);
                         tma_load_2d(sQ + a * TILE_BYTES, &tmQ, &B->q_full[a], h * HD, q0 + a * QT);
                     }
@@ -138,10 +138,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     for (int j = 0; j < nkv; ++j) {
                         const int kv0 = (SPARSE ? pairs[j] : j) * KT;
                         uint8_t* sk = sKV + st * 2 * TILE_BYTES;
-                        mbar_wait(&B->k_empty[st], ph ^ 1);
+                        mbar_wait_parked(&B->k_empty[st], ph ^ 1);
                         mbar_expect_tx(&B->k_full[st], TILE_BYTES);
                         tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, kv0);
-                        mbar_wait(&B->v_empty[st], ph ^ 1);
+                        mbar_wait_parked(&B->v_empty[st], ph ^ 1);
                         mbar_expect_tx(&B->v_full[st], TILE_BYTES);
                         tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, kv0);
                         if (++st == KV_STAGES) {
@@ -172,7 +172,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 int i = 0;
 
                 auto issue_qk = [&](bool last_of_item) {
-                    mbar_wait(&B->k_full[kst], kph);
+                    mbar_wait_parked(&B->k_full[kst], kph);
                     tc_fence_after();
                     const uint32_t ka = skv_addr + kst * 2 * TILE_BYTES;
 #pragma unroll
@@ -190,17 +190,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
                     const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
                     // S_a(0) = Q_a K_0^T: needs Q_a and the S buffer (drained at the last tile of the previous item)
-                    mbar_wait(&B->q_full[a], i & 1);
-                    if (g > 0) mbar_wait(&B->s_free[a], (g - 1) & 1);
+                    mbar_wait_parked(&B->q_full[a], i & 1);
+                    if (g > 0) mbar_wait_parked(&B->s_free[a], (g - 1) & 1);
                     issue_qk(nkv == 1);
                     for (int j = 0; j < nkv; ++j, ++g) {
                         if (j + 1 < nkv) {
-                            mbar_wait(&B->s_free[a], g & 1);
+                            mbar_wait_parked(&B->s_free[a], g & 1);
                             issue_qk(j + 2 == nkv);
                         }
-                        if (j == 0) mbar_wait(&B->o_free[a], (i & 1) ^ 1);
-                        mbar_wait(&B->p_ready[a], g & 1);
-                        mbar_wait(&B->v_full[vst], vph);
+                        if (j == 0) mbar_wait_parked(&B->o_free[a], (i & 1) ^ 1);
+                        mbar_wait_parked(&B->p_ready[a], g & 1);
+                        mbar_wait_parked(&B->v_full[vst], vph);
                         tc_fence_after();
                         const uint32_t va = skv_addr + vst * 2 * TILE_BYTES + TILE_BYTES;
 #pragma unroll
@@ -477,6 +477,8 @@ build_items_kernel(const int32_t* __restrict__ kv_count, const int32_t* __restri
 
 AttnSparseWs g_sparse_ws;
 
+}  // namespace
+
 int ensure_sparse_ws(AttnSparseWs& w, size_t items, size_t max_pairs) {
     if (w.items >= items && w.max_pairs >= max_pairs) return K5_OK;
     if (w.count) cudaFree(w.count);
@@ -494,6 +496,9 @@ int ensure_sparse_ws(AttnSparseWs& w, size_t items, size_t max_pairs) {
     return K5_OK;
 }
 
+namespace {
+
+constexpr int ATT_IMPL_DEFAULT = 2;      // 2 = two 128-row query tiles x 128-row KV tiles (this file), 4 = attention4.cu
 constexpr int ATT_NPOLY_DEFAULT = 0;
 constexpr int ATT_STAGGER_DEFAULT = 0;
 
@@ -542,8 +547,11 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
-    static int npoly = -1, stagger = 0;
+    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, nq4 = 2;
     if (npoly < 0) {
+        if (const char* im = getenv("K5_ATTN_IMPL")) impl = atoi(im);
+        if (impl != 2 && impl != 4) impl = ATT_IMPL_DEFAULT;
+        if (const char* nq = getenv("K5_ATTN_NQ")) nq4 = atoi(nq) == 3 ? 3 : 2;
         const char* sg = getenv("K5_ATTN_STAGGER");
         stagger = sg ? atoi(sg) : ATT_STAGGER_DEFAULT;
         // fraction of the exponentials evaluated on the FMA pipe (pairs out of every 8); tuning knob only
@@ -561,6 +569,12 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.ldo = ldo;
     p.kv_count = kv_count;
     p.kv_index = kv_index;
+    p.item_count = nullptr;
+    p.item_pairs = nullptr;
+    p.item_mask = nullptr;
+    p.max_pairs = 0;
+    p.stagger = stagger;
+    if (impl == 4) return attention_fwd_v4(Q, ldq, K, ldk, V, ldv, p, nq4, st, ws_in ? *ws_in : g_sparse_ws);
     const int n_qpairs = (Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * heads;
     const int grid = n_items < sm_count() ? n_items : sm_count();

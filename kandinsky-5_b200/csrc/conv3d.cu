@@ -122,7 +122,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 for (int tap = 0; tap < 27; ++tap) {
                     const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
                     for (int cb = 0; cb < cblocks; ++cb, ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_wait_parked(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                         // padded coordinates: output (t, h, w), tap (kt, kh, kw) reads xpad[t + kt, h + kh, w + kw]
@@ -148,11 +148,11 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait_parked(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * MT * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait_parked(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + MT * Cfg::A_BYTES;

@@ -93,7 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int m0 = (tile / n_tiles_n) * BM;
                 const int n0 = (tile % n_tiles_n) * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait_parked(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
@@ -115,11 +115,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait_parked(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait_parked(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + Cfg::A_BYTES;

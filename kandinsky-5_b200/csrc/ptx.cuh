@@ -75,6 +75,72 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Address-based variants (shared::cta byte address kept in a register): inner loops that touch many barriers use
+// these so the generic -> shared conversion is not re-materialised at every use.
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_a(bar, parity)) {
+        if (++spins > K5_SPIN_LIMIT) __trap();
+    }
+}
+
+// Wait used by the single-thread roles (TMA producer, MMA issuers), whose waits last a whole tile: the suspend-time
+// hint keeps the thread parked in hardware instead of re-issuing the poll every ~40 cycles, so the poll loop does
+// not take issue slots from the softmax warps that share its scheduler (measured: 33 polls x 6 instructions per tile
+// from the producer alone, +39 % instructions on that scheduler).
+#ifndef K5_PARK
+#define K5_PARK 1
+#endif
+__device__ __forceinline__ void mbar_wait_parked_a(uint32_t bar, uint32_t parity) {
+    if (!K5_PARK) return mbar_wait_a(bar, parity);
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(100000u)
+            : "memory");
+        if (ok) return;
+        if (++spins > K5_SPIN_LIMIT) __trap();
+    }
+}
+
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) { mbar_wait_parked_a(smem_u32(bar), parity); }
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -84,6 +150,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
 
@@ -124,6 +197,10 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // TMEM -> registers, 32 lanes x 32 bit, N consecutive columns; thread t of the warp reads lane
@@ -246,6 +323,12 @@ __device__ __forceinline__ uint64_t fma_f32x2_v(uint64_t a, uint64_t b, uint64_t
     asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+// x * (0.125 * log2(e)) + c with the scale as an immediate (FFMA imm-form issues at twice the 3-register rate)
+__device__ __forceinline__ float fma_scale_imm_v(float x, float c) {
+    float r;
+    asm volatile("fma.rn.f32 %0, %1, 0f3E38AA3B, %2;" : "=f"(r) : "f"(x), "f"(c));
+    return r;
+}
 __device__ __forceinline__ uint64_t add_f32x2_v(uint64_t a, uint64_t b) {
     uint64_t r;
     asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -259,6 +342,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2_v(float lo, float hi) {
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+__device__ __forceinline__ float max3_v(float a, float b, float c) {
+    float r;
+    asm volatile("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
 

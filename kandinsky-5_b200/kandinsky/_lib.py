@@ -5,7 +5,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libk5.so")
+# K5_LIB_PATH selects another build of the same library (A/B of compile-time tuning knobs); there is still no fallback
+LIB_PATH = os.environ.get("K5_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libk5.so")
 
 K5_OK, K5_ERR_INVALID, K5_ERR_CUDA, K5_ERR_STATE, K5_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 EPI_STORE, EPI_GELU, EPI_GATE, EPI_HEADS = 0, 1, 2, 3

@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""A/B of the attention kernel variants on one B200 (not a pytest file).  The variant knobs (K5_ATTN_IMPL,
+K5_ATTN_PROBE, ...) are read once per process, so every variant runs in its own subprocess: a correctness check
+against a torch fp32 restatement (dense with a ragged KV tail, cross-attention shape, block-sparse against the masked
+dense result) followed by the isolated-kernel timing at the 5 s size (S = 47 616, 28 heads).
+Usage: python tests/gpu_attn_variants.py [name=ENV1:val,ENV2:val ...]"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "kandinsky-5_b200"))
+
+DEFAULT = ["v2=K5_ATTN_IMPL:2", "v3=K5_ATTN_IMPL:3,K5_ATTN_PROBE:0", "v3probe=K5_ATTN_IMPL:3,K5_ATTN_PROBE:1"]
+
+
+def child():
+    import torch
+
+    from kandinsky import ops
+
+    def rel(a, b):
+        a, b = a.float(), b.float()
+        return float((a - b).norm() / b.norm())
+
+    def ref(q, k, v, heads, mask=None):
+        Sq, Sk = q.shape[0], k.shape[0]
+        q4 = q.float().reshape(Sq, heads, 64).transpose(0, 1)
+        k4 = k.float().reshape(Sk, heads, 64).transpose(0, 1)
+        v4 = v.float().reshape(Sk, heads, 64).transpose(0, 1)
+        s = q4 @ k4.transpose(1, 2) * 0.125
+        if mask is not None:
+            s = s.masked_fill(~mask, float("-inf"))
+        return (torch.softmax(s, -1) @ v4).transpose(0, 1).reshape(Sq, heads * 64)
+
+    name = os.environ["K5_VARIANT_NAME"]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    errs = []
+    for (Sq, Sk, heads) in [(64, 64, 2), (1000, 777, 3), (2304, 2304, 2), (4000, 256, 4), (3 * 384 + 5, 37, 2)]:
+        q = torch.randn(Sq, heads * 64, device="cuda", generator=g).bfloat16()
+        k = torch.randn(Sk, heads * 64, device="cuda", generator=g).bfloat16()
+        v = torch.randn(Sk, heads * 64, device="cuda", generator=g).bfloat16()
+        out = ops.attention(q, k, v, heads)
+        torch.cuda.synchronize()
+        errs.append(rel(out, ref(q, k, v, heads)))
+    # large logits: the lazy rescale has to fire
+    q = (torch.randn(1536, 128, device="cuda", generator=g) * 6).bfloat16()
+    k = (torch.randn(1536, 128, device="cuda", generator=g) * 6).bfloat16()
+    v = torch.randn(1536, 128, device="cuda", generator=g).bfloat16()
+    errs.append(rel(ops.attention(q, k, v, 2), ref(q, k, v, 2)))
+    # block-sparse against the masked dense result
+    S, heads = 1600, 2                      # 25 blocks: the last query item is partial for both kernels
+    nb = S // 64
+    q = torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16()
+    k = torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16()
+    v = torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16()
+    sel = torch.rand(heads, nb, nb, device="cuda", generator=g) < 0.3
+    sel |= torch.eye(nb, device="cuda", dtype=torch.bool)[None]
+    cnt = sel.sum(-1).to(torch.int32)
+    idx = torch.argsort((~sel).to(torch.int8), dim=-1, stable=True).to(torch.int32)
+    out = ops.attention(q, k, v, heads, kv_count=cnt.contiguous(), kv_index=idx.contiguous())
+    full = sel.repeat_interleave(64, 1).repeat_interleave(64, 2)
+    errs.append(rel(out, ref(q, k, v, heads, full)))
+    ok = all(e < 8e-3 for e in errs[:5]) and errs[5] < 1e-2 and errs[6] < 8e-3
+    print(f"{name}: parity rel-L2 {' '.join(f'{e:.2e}' for e in errs)} -> {'OK' if ok else 'FAIL'}", flush=True)
+    if not ok and not os.environ.get("K5_VARIANT_NOCHECK"):
+        sys.exit(1)
+    S, heads, D = int(os.environ.get("K5_BENCH_S", 47616)), 28, 1792
+    qkv = torch.randn(S, 3 * D, device="cuda", generator=g).bfloat16()
+    o = torch.empty(S, D, device="cuda", dtype=torch.bfloat16)
+
+    def run():
+        ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads, out=o)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(8):
+        run()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 8
+    print(f"{name}: attn S={S} h={heads}: {ms:.2f} ms = {4.0 * S * S * D / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
+def main():
+    if os.environ.get("K5_VARIANT_NAME"):
+        return child()
+    specs = sys.argv[1:] or DEFAULT
+    for spec in specs:
+        name, _, envs = spec.partition("=")
+        env = dict(os.environ, K5_VARIANT_NAME=name)
+        for kv in filter(None, envs.split(",")):
+            k, _, v = kv.partition(":")
+            env[k] = v
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, timeout=240)
+            if r.returncode != 0:
+                print(f"{name}: exit code {r.returncode}", flush=True)
+        except subprocess.TimeoutExpired:
+            print(f"{name}: TIMEOUT", flush=True)
+
+
+if __name__ == "__main__":
+    main()
