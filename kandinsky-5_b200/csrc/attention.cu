@@ -129,7 +129,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     const int h = item / n_qpairs;
                     const int q0 = (item % n_qpairs) * 2 * QT;
                     for (int a = 0; a < 2; ++a) {
-                        mbar_wait_parked(&B->q_empty[a], (i & 1) ^ 1);
+                        mbar_wait(&B->q_empty[a], (i & 1) ^ 1);
                         mbar_expect_tx(&B->q_full[a], TILE_BYTES);
                         tma_load_2d(sQ + a * TILE_BYTES, &tmQ, &B->q_full[a], h * HD, q0 + a * QT);
                     }
@@ -138,10 +138,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     for (int j = 0; j < nkv; ++j) {
                         const int kv0 = (SPARSE ? pairs[j] : j) * KT;
                         uint8_t* sk = sKV + st * 2 * TILE_BYTES;
-                        mbar_wait_parked(&B->k_empty[st], ph ^ 1);
+                        mbar_wait(&B->k_empty[st], ph ^ 1);
                         mbar_expect_tx(&B->k_full[st], TILE_BYTES);
                         tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, kv0);
-                        mbar_wait_parked(&B->v_empty[st], ph ^ 1);
+                        mbar_wait(&B->v_empty[st], ph ^ 1);
                         mbar_expect_tx(&B->v_full[st], TILE_BYTES);
                         tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, kv0);
                         if (++st == KV_STAGES) {
@@ -172,7 +172,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 int i = 0;
 
                 auto issue_qk = [&](bool last_of_item) {
-                    mbar_wait_parked(&B->k_full[kst], kph);
+                    mbar_wait(&B->k_full[kst], kph);
                     tc_fence_after();
                     const uint32_t ka = skv_addr + kst * 2 * TILE_BYTES;
 #pragma unroll
@@ -190,17 +190,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
                     const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
                     // S_a(0) = Q_a K_0^T: needs Q_a and the S buffer (drained at the last tile of the previous item)
-                    mbar_wait_parked(&B->q_full[a], i & 1);
-                    if (g > 0) mbar_wait_parked(&B->s_free[a], (g - 1) & 1);
+                    mbar_wait(&B->q_full[a], i & 1);
+                    if (g > 0) mbar_wait(&B->s_free[a], (g - 1) & 1);
                     issue_qk(nkv == 1);
                     for (int j = 0; j < nkv; ++j, ++g) {
                         if (j + 1 < nkv) {
-                            mbar_wait_parked(&B->s_free[a], g & 1);
+                            mbar_wait(&B->s_free[a], g & 1);
                             issue_qk(j + 2 == nkv);
                         }
-                        if (j == 0) mbar_wait_parked(&B->o_free[a], (i & 1) ^ 1);
-                        mbar_wait_parked(&B->p_ready[a], g & 1);
-                        mbar_wait_parked(&B->v_full[vst], vph);
+                        if (j == 0) mbar_wait(&B->o_free[a], (i & 1) ^ 1);
+                        mbar_wait(&B->p_ready[a], g & 1);
+                        mbar_wait(&B->v_full[vst], vph);
                         tc_fence_after();
                         const uint32_t va = skv_addr + vst * 2 * TILE_BYTES + TILE_BYTES;
 #pragma unroll

@@ -326,9 +326,13 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);
             float pc[16], pp[16];
             auto drain = [&](int c, int q) {              // results of quarter c-1: row sum + bf16 pack in place
+#ifndef K5_V4_NOSUM
                 const uint64_t pr = pack_f32x2(pp[2 * q], pp[2 * q + 1]);
                 if (q & 1) sum_b = add_f32x2_v(sum_b, pr);
                 else sum_a = add_f32x2_v(sum_a, pr);
+#else
+                if (c == 1 && q == 0) sum_a = pack_f32x2(pp[0], pp[1]);   // timing experiment only
+#endif
                 cur[8 * (c - 1) + q] = pack_bf16x2_v(pp[2 * q], pp[2 * q + 1]);
             };
             const uint32_t nb = (cnt + 1) & 1, nph = ((cnt + 1) >> 1) & 1;
