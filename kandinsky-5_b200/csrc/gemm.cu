@@ -16,6 +16,8 @@
 //       EPI_HEADS : bf16(acc + bias) -> per-head RMSNorm (fp32) -> bf16 -> RoPE (fp32) -> bf16
 //                                                                           nn.py:246-250, 35-40
 // Rounding points follow SURVEY.md Appendix A.
+#include <cstdlib>
+
 #include "common.h"
 #include "gemm.h"
 #include "ptx.cuh"
@@ -26,6 +28,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr bool GEMM_CLUSTER_DEFAULT = true;    // +2 ... +5 % at K = 1792 (profiles/r1_gemm_cluster.md)
 constexpr int GEMM_THREADS = 384;     // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue, two per TMEM lane quarter
 
 template <int BN>
@@ -41,7 +44,26 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int EPI>
+// Static tile schedule.  CL = 1: tile = blockIdx.x + i * gridDim.x, N fastest.  CL = 2 (thread-block cluster of two
+// CTAs): the pair works on the two M tiles of one 256-row "super tile" and the same N tile, so both need the same W
+// tile: each CTA fetches one half of it and TMA multicasts it into both shared memories - 32 KB instead of 48 KB
+// of L2 -> SM traffic per CTA and k-block at BN = 256.  (At 128 x 256 x 64 per 512 tensor cycles the single-CTA kernel
+// asks L2 for ~13 TB/s over 148 SMs, which is what the L2 can deliver; profiles/r1_gemm_cluster.md.)
+template <int CL>
+struct TileIter {
+    int i, step, count, n_tiles_n, crank;
+    __device__ TileIter(int n_tiles_m, int n_tiles_n_, int crank_) : n_tiles_n(n_tiles_n_), crank(crank_) {
+        i = blockIdx.x / CL;
+        step = gridDim.x / CL;
+        count = ((n_tiles_m + CL - 1) / CL) * n_tiles_n;
+    }
+    __device__ bool valid() const { return i < count; }
+    __device__ void next() { i += step; }
+    __device__ int m0() const { return ((i / n_tiles_n) * CL + crank) * BM; }
+    __device__ int n0(int BN) const { return (i % n_tiles_n) * BN; }
+};
+
+template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue e) {
@@ -60,8 +82,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int n_tiles_n = N / BN;
     const int n_tiles_m = (M + BM - 1) / BM;
-    const int num_tiles = n_tiles_m * n_tiles_n;
     const int nkb = (K + BK - 1) / BK;
+    const int crank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA);
@@ -70,7 +92,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);      // CL > 1: the peer's multicast also lands in this stage, so both MMA warps free it
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
@@ -81,6 +103,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -89,15 +112,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles_n) * BM;
-                const int n0 = (tile % n_tiles_n) * BN;
+            for (TileIter<CL> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next()) {
+                const int m0 = t.m0();
+                const int n0 = t.n0(BN);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait_parked(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    if constexpr (CL > 1) {
+                        // tmB's box is BN / CL rows here: this CTA's slice of the W tile goes to every CTA of the pair
+                        tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / CL), &tmB, &full[stage], kb * BK,
+                                       n0 + crank * (BN / CL), static_cast<uint16_t>((1u << CL) - 1u));
+                    } else {
+                        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -112,7 +141,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (TileIter<CL> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next(), ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait_parked(&tempty[acc], acc_phase ^ 1);
@@ -129,7 +158,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint64_t bd = umma_desc_sw128(sb + k * 32, 0, 1024);
                         umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);     // smem slot reusable once these MMAs have read it
+                    // smem slot reusable once these MMAs have read it (in both CTAs when the W tile is shared)
+                    if constexpr (CL > 1) umma_commit_mc(&empty[stage], static_cast<uint16_t>((1u << CL) - 1u));
+                    else umma_commit(&empty[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -146,11 +177,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int chalf = (warp - 4) >> 2;
         const int lane = threadIdx.x & 31;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (TileIter<CL> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next(), ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / n_tiles_n) * BM;
-            const int n0 = (tile % n_tiles_n) * BN;
+            const int m0 = t.m0();
+            const int n0 = t.n0(BN);
             const int row = m0 + wq * 32 + lane;
             const bool row_ok = row < M;
             // RoPE angles depend on the row only: fetch this row's 32 (cos, sin) pairs once per tile, BEFORE waiting for
@@ -349,36 +380,71 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast to it or free its stages
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CL>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
-    static bool configured = false;
-    auto kern = gemm_bf16_kernel<BN, EPI>;
-    if (!configured) {
+    static int max_ctas = 0;           // CTAs that can be resident at once (whole clusters only when CL > 1)
+    auto kern = gemm_bf16_kernel<BN, EPI, CL>;
+    if (max_ctas == 0) {
         K5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
+        max_ctas = sm_count();
+        if (CL > 1) {
+            // clusters live inside one GPC; a GPC with an odd SM count leaves one SM out
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(static_cast<unsigned>(sm_count() / CL * CL));
+            q.blockDim = dim3(GEMM_THREADS);
+            q.dynamicSmemBytes = Cfg::SMEM_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = CL;
+            qa[0].val.clusterDim.y = 1;
+            qa[0].val.clusterDim.z = 1;
+            q.attrs = qa;
+            q.numAttrs = 1;
+            int n_clusters = 0;
+            K5_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q));
+            K5_REQUIRE(n_clusters > 0, "GEMM: no thread-block cluster fits this device");
+            max_ctas = n_clusters * CL;
+        }
     }
-    const int tiles = ((M + BM - 1) / BM) * (N / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, e);
+    const int units = (((M + BM - 1) / BM + CL - 1) / CL) * (N / BN) * CL;
+    const int grid = units < max_ctas ? units : max_ctas;
+    if (CL == 1) {
+        kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, e);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        K5_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, e));
+    }
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }
 
-template <int BN>
+template <int BN, int CL>
 int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& e,
                cudaStream_t st) {
     switch (epi) {
-        case EPI_STORE: return launch<BN, EPI_STORE>(tmA, tmB, M, N, K, e, st);
-        case EPI_GELU: return launch<BN, EPI_GELU>(tmA, tmB, M, N, K, e, st);
-        case EPI_GATE: return launch<BN, EPI_GATE>(tmA, tmB, M, N, K, e, st);
-        case EPI_HEADS: return launch<BN, EPI_HEADS>(tmA, tmB, M, N, K, e, st);
+        case EPI_STORE: return launch<BN, EPI_STORE, CL>(tmA, tmB, M, N, K, e, st);
+        case EPI_GELU: return launch<BN, EPI_GELU, CL>(tmA, tmB, M, N, K, e, st);
+        case EPI_GATE: return launch<BN, EPI_GATE, CL>(tmA, tmB, M, N, K, e, st);
+        case EPI_HEADS: return launch<BN, EPI_HEADS, CL>(tmA, tmB, M, N, K, e, st);
     }
     set_last_error("unknown GEMM epilogue");
     return K5_ERR_INVALID;
@@ -406,12 +472,24 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
         K5_REQUIRE(e.peers.n == 0, "GEMM: the peer scatter belongs to the head epilogue");
     }
     const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+    // CTA pairs sharing the W tile pay as soon as there are two M tiles to pair (K5_GEMM_CLUSTER=0/1 overrides: tuning)
+    static int cluster_env = -1;
+    if (cluster_env < 0) {
+        const char* ev = getenv("K5_GEMM_CLUSTER");
+        cluster_env = ev ? (atoi(ev) != 0 ? 1 : 0) : 2;
+    }
+    const bool pair = cluster_env == 2 ? (GEMM_CLUSTER_DEFAULT && M > BM) : (cluster_env == 1);
     CUtensorMap tmA, tmB;
     K5_TRY(make_tmap_2d_bf16(&tmA, A, M, K, lda, BM));
-    K5_TRY(make_tmap_2d_bf16(&tmB, W, N, K, ldw, BN));
-    if (BN == 256) return launch_epi<256>(epi, tmA, tmB, M, N, K, e, st);
-    if (BN == 128) return launch_epi<128>(epi, tmA, tmB, M, N, K, e, st);
-    return launch_epi<64>(epi, tmA, tmB, M, N, K, e, st);
+    K5_TRY(make_tmap_2d_bf16(&tmB, W, N, K, ldw, pair ? BN / 2 : BN));
+    if (pair) {
+        if (BN == 256) return launch_epi<256, 2>(epi, tmA, tmB, M, N, K, e, st);
+        if (BN == 128) return launch_epi<128, 2>(epi, tmA, tmB, M, N, K, e, st);
+        return launch_epi<64, 2>(epi, tmA, tmB, M, N, K, e, st);
+    }
+    if (BN == 256) return launch_epi<256, 1>(epi, tmA, tmB, M, N, K, e, st);
+    if (BN == 128) return launch_epi<128, 1>(epi, tmA, tmB, M, N, K, e, st);
+    return launch_epi<64, 1>(epi, tmA, tmB, M, N, K, e, st);
 }
 
 }  // namespace k5

@@ -48,6 +48,8 @@ def main():
         fl = 2.0 * M * N * K
         print(f"gemm {epi:6s} M={M} N={N} K={K}: k5 {ms:.3f} ms = {fl / ms / 1e9:.0f} TFLOP/s | torch.matmul {ms_t:.3f} ms = {fl / ms_t / 1e9:.0f} TFLOP/s", flush=True)
         del a, w, out
+    if only == "gemm":
+        return
     heads = 28
     qkv = torch.randn(S, 3 * D, device=dev).bfloat16()
     o = torch.empty(S, D, device=dev, dtype=torch.bfloat16)
