@@ -28,15 +28,18 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr bool GEMM_CLUSTER_DEFAULT = true;    // +2 ... +5 % at K = 1792 (profiles/r1_gemm_cluster.md)
+// 0 = single CTA, 1 = CTA pair + W multicast, 3 = CTA pair + 2-SM MMA (K5_GEMM_CLUSTER overrides; profiles/r1_gemm_cluster.md)
+constexpr int GEMM_CLUSTER_DEFAULT = 3;
 constexpr int GEMM_THREADS = 384;     // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue, two per TMEM lane quarter
 
-template <int BN>
+// CL: 1 = single CTA; 2 = CTA pair, W tile multicast, cta_group::1 MMAs; 3 = CTA pair, ONE cta_group::2 MMA per pair
+// (each CTA keeps only its half of the W tile).
+template <int BN, int CL = 1>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (CL == 3 ? BN / 2 : BN) * BK * 2;      // bytes of W held per CTA and stage
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = CL == 3 ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int XPOSE_BYTES = 8 * 32 * 128;   // per epilogue warp: 32 rows x 128 B, for the peer scatter
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XPOSE_BYTES;
@@ -67,8 +70,10 @@ template <int BN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  GemmEpilogue e) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CL>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int NC = CL == 1 ? 1 : 2;          // CTAs per cluster
+    constexpr bool MMA2 = CL == 3;               // 2-SM MMA
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -83,7 +88,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_tiles_n = N / BN;
     const int n_tiles_m = (M + BM - 1) / BM;
     const int nkb = (K + BK - 1) / BK;
-    const int crank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int crank = NC > 1 ? static_cast<int>(cluster_ctarank()) : 0;
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA);
@@ -92,18 +97,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CL);      // CL > 1: the peer's multicast also lands in this stage, so both MMA warps free it
+            mbar_init(&empty[s], CL == 2 ? 2 : 1);   // CL = 2: the peer's multicast also lands here, both MMA warps free it
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 256);
+            mbar_init(&tempty[s], MMA2 ? 512 : 256);   // 2-SM MMA: the leader's barrier collects both CTAs' epilogues
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 2) {
+        if constexpr (MMA2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+        else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is sent to them
+    if constexpr (NC > 1) cluster_sync_all();   // the peer's barriers exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -112,18 +120,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (TileIter<CL> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next()) {
+            for (TileIter<NC> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next()) {
                 const int m0 = t.m0();
                 const int n0 = t.n0(BN);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait_parked(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    if constexpr (MMA2) {
+                        // both CTAs load their A tile and their half of the W tile into their own shared memory; the
+                        // bytes of both are counted on the leader's barrier, which only the leader arms
+                        if (crank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                        tma_load_2d_2sm(sa, &tmA, &full[stage], kb * BK, m0);
+                        tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, n0 + crank * (BN / 2));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-                    if constexpr (CL > 1) {
-                        // tmB's box is BN / CL rows here: this CTA's slice of the W tile goes to every CTA of the pair
-                        tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / CL), &tmB, &full[stage], kb * BK,
-                                       n0 + crank * (BN / CL), static_cast<uint16_t>((1u << CL) - 1u));
+                    if constexpr (CL == 2) {
+                        // tmB's box is BN / 2 rows here: this CTA's slice of the W tile goes to every CTA of the pair
+                        tma_load_2d_mc(sa + Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2), &tmB, &full[stage], kb * BK,
+                                       n0 + crank * (BN / 2), static_cast<uint16_t>(3));
                     } else {
                         tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, n0);
                     }
@@ -135,13 +155,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        // ===================== MMA issuer (2-SM MMA: the leader CTA issues for the pair) =====================
+        if ((!MMA2 || crank == 0) && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(MMA2 ? 2 * BM : BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (TileIter<CL> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next(), ++it) {
+            for (TileIter<NC> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next(), ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait_parked(&tempty[acc], acc_phase ^ 1);
@@ -156,17 +176,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ad = umma_desc_sw128(sa + k * 32, 0, 1024);
                         const uint64_t bd = umma_desc_sw128(sb + k * 32, 0, 1024);
-                        umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (MMA2) umma_ss_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    // smem slot reusable once these MMAs have read it (in both CTAs when the W tile is shared)
-                    if constexpr (CL > 1) umma_commit_mc(&empty[stage], static_cast<uint16_t>((1u << CL) - 1u));
+                    // smem slot reusable once these MMAs have read it (in both CTAs when the pair shares the stage)
+                    if constexpr (MMA2) umma_commit_2sm_mc(&empty[stage], static_cast<uint16_t>(3));
+                    else if constexpr (CL == 2) umma_commit_mc(&empty[stage], static_cast<uint16_t>(3));
                     else umma_commit(&empty[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[acc]);           // accumulator complete
+                // accumulator complete (2-SM MMA: each CTA's epilogue waits on its own copy of the barrier)
+                if constexpr (MMA2) umma_commit_2sm_mc(&tfull[acc], static_cast<uint16_t>(3));
+                else umma_commit(&tfull[acc]);
             }
         }
     } else if (warp >= 4) {
@@ -177,7 +201,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int chalf = (warp - 4) >> 2;
         const int lane = threadIdx.x & 31;
         int it = 0;
-        for (TileIter<CL> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next(), ++it) {
+        for (TileIter<NC> t(n_tiles_m, n_tiles_n, crank); t.valid(); t.next(), ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = t.m0();
@@ -374,36 +398,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            if constexpr (MMA2) mbar_arrive_leader(&tempty[acc]);
+            else mbar_arrive(&tempty[acc]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast to it or free its stages
+    if constexpr (NC > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast to it or free its stages
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if constexpr (MMA2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+        else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
 template <int BN, int EPI, int CL>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
-    static int max_ctas = 0;           // CTAs that can be resident at once (whole clusters only when CL > 1)
+    using Cfg = GemmCfg<BN, CL>;
+    constexpr int NC = CL == 1 ? 1 : 2;
+    static int max_ctas = 0;           // CTAs that can be resident at once (whole clusters only when NC > 1)
     auto kern = gemm_bf16_kernel<BN, EPI, CL>;
     if (max_ctas == 0) {
         K5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         max_ctas = sm_count();
-        if (CL > 1) {
+        if (NC > 1) {
             // clusters live inside one GPC; a GPC with an odd SM count leaves one SM out
             cudaLaunchConfig_t q = {};
-            q.gridDim = dim3(static_cast<unsigned>(sm_count() / CL * CL));
+            q.gridDim = dim3(static_cast<unsigned>(sm_count() / NC * NC));
             q.blockDim = dim3(GEMM_THREADS);
             q.dynamicSmemBytes = Cfg::SMEM_BYTES;
             cudaLaunchAttribute qa[1];
             qa[0].id = cudaLaunchAttributeClusterDimension;
-            qa[0].val.clusterDim.x = CL;
+            qa[0].val.clusterDim.x = NC;
             qa[0].val.clusterDim.y = 1;
             qa[0].val.clusterDim.z = 1;
             q.attrs = qa;
@@ -411,12 +438,12 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, 
             int n_clusters = 0;
             K5_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q));
             K5_REQUIRE(n_clusters > 0, "GEMM: no thread-block cluster fits this device");
-            max_ctas = n_clusters * CL;
+            max_ctas = n_clusters * NC;
         }
     }
-    const int units = (((M + BM - 1) / BM + CL - 1) / CL) * (N / BN) * CL;
+    const int units = (((M + BM - 1) / BM + NC - 1) / NC) * (N / BN) * NC;
     const int grid = units < max_ctas ? units : max_ctas;
-    if (CL == 1) {
+    if (NC == 1) {
         kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, e);
     } else {
         cudaLaunchConfig_t cfg = {};
@@ -426,7 +453,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, 
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.x = NC;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
@@ -472,16 +499,21 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
         K5_REQUIRE(e.peers.n == 0, "GEMM: the peer scatter belongs to the head epilogue");
     }
     const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
-    // CTA pairs sharing the W tile pay as soon as there are two M tiles to pair (K5_GEMM_CLUSTER=0/1 overrides: tuning)
+    // CTA pairs pay as soon as there are two M tiles to pair (K5_GEMM_CLUSTER = 0 / 1 / 3 overrides: tuning)
     static int cluster_env = -1;
     if (cluster_env < 0) {
         const char* ev = getenv("K5_GEMM_CLUSTER");
-        cluster_env = ev ? (atoi(ev) != 0 ? 1 : 0) : 2;
+        cluster_env = ev ? (atoi(ev) == 3 ? 3 : (atoi(ev) != 0 ? 1 : 0)) : 2;
     }
-    const bool pair = cluster_env == 2 ? (GEMM_CLUSTER_DEFAULT && M > BM) : (cluster_env == 1);
+    const bool pair = cluster_env == 2 ? (GEMM_CLUSTER_DEFAULT != 0 && M > BM) : (cluster_env >= 1);
     CUtensorMap tmA, tmB;
     K5_TRY(make_tmap_2d_bf16(&tmA, A, M, K, lda, BM));
     K5_TRY(make_tmap_2d_bf16(&tmB, W, N, K, ldw, pair ? BN / 2 : BN));
+    if (pair && (cluster_env == 3 || (cluster_env == 2 && GEMM_CLUSTER_DEFAULT == 3))) {   // 2-SM MMA
+        if (BN == 256) return launch_epi<256, 3>(epi, tmA, tmB, M, N, K, e, st);
+        if (BN == 128) return launch_epi<128, 3>(epi, tmA, tmB, M, N, K, e, st);
+        return launch_epi<64, 3>(epi, tmA, tmB, M, N, K, e, st);
+    }
     if (pair) {
         if (BN == 256) return launch_epi<256, 2>(epi, tmA, tmB, M, N, K, e, st);
         if (BN == 128) return launch_epi<128, 2>(epi, tmA, tmB, M, N, K, e, st);
