@@ -11,6 +11,8 @@
 // Everything else is the pipeline of gemm.cu: multi-stage TMA ring, one elected MMA thread, fp32 accumulators
 // double-buffered in TMEM, 4 epilogue warps (thread = output position) that add the bias, round to bf16, add the
 // residual (bf16 + bf16 like the reference's tensor add) and store channels-last.
+#include <cstdlib>
+
 #include "common.h"
 #include "conv3d.h"
 #include "ptx.cuh"
@@ -21,14 +23,17 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int CONV_CLUSTER_DEFAULT = 1;   // VAE decode -5.4 % (profiles/r1_gemm_cluster.md)
 
 // MT = M tiles (128 positions each) that share one weight tile: with 128 output channels a 128 x 128 tile pulls
 // 128 B / clk / SM of operands out of L2 (measured 594 TFLOP/s); two position tiles per weight tile cut the
 // weight traffic and the TMA requests per FLOP to the level of the 128 x 256 tile.
-template <int BN, int MT>
+// CL: 1 = single CTA; 3 = CTA pair driven by ONE cta_group::2 MMA (M = 256: each CTA supplies its 128 positions and
+// keeps only its half of the weight tile), as in gemm.cu.
+template <int BN, int MT, int CL = 1>
 struct ConvCfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (CL == 3 ? BN / 2 : BN) * BK * 2;    // bytes of the weight tile held per CTA and stage
     static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
     static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) < 8 ? (200 * 1024 / STAGE_BYTES) : 8;
     static constexpr int TMEM_COLS = 2 * MT * BN;
@@ -48,6 +53,17 @@ struct ConvParams {
     int ldo;
 };
 
+// 2-SM form: lands in this CTA's shared memory, completes on the leader CTA's mbarrier (ptx.cuh)
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & K5_PEER_BIT_MASK), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -57,11 +73,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int CL>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvParams p) {
-    using Cfg = ConvCfg<BN, MT>;
+    using Cfg = ConvCfg<BN, MT, CL>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int NC = CL == 1 ? 1 : 2;          // CTAs per cluster
+    constexpr bool MMA2 = CL == 3;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -76,7 +94,10 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int tiles_per_frame = p.tiles_w * p.tiles_h;
     const int n_tiles_m = ((p.T + p.bt - 1) / p.bt) * tiles_per_frame;
     const int n_groups_m = (n_tiles_m + MT - 1) / MT;         // groups of MT consecutive position tiles
-    const int num_tiles = n_groups_m * n_tiles_n;
+    // work unit of a cluster = NC consecutive groups x one weight tile; CTA `crank` takes group unit_m * NC + crank
+    const int num_units = ((n_groups_m + NC - 1) / NC) * n_tiles_n;
+    const int crank = NC > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int unit0 = blockIdx.x / NC, unit_step = gridDim.x / NC;
     const int cblocks = p.Cin / BK;
     const int nkb = 27 * cblocks;
 
@@ -91,13 +112,17 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 128 * MT);
+            mbar_init(&tempty[s], 128 * MT * NC);      // 2-SM MMA: the leader's barrier collects both CTAs' epilogues
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 2) {
+        if constexpr (MMA2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+        else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
+    if constexpr (NC > 1) cluster_sync_all();    // the peer's barriers exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -106,9 +131,9 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mg = tile / n_tiles_n;
-                const int n0 = (tile % n_tiles_n) * BN;
+            for (int unit = unit0; unit < num_units; unit += unit_step) {
+                const int mg = (unit / n_tiles_n) * NC + crank;
+                const int n0 = (unit % n_tiles_n) * BN;
                 int t[MT], h0[MT], w0[MT];
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
@@ -124,12 +149,22 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                     for (int cb = 0; cb < cblocks; ++cb, ++kb) {
                         mbar_wait_parked(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                         // padded coordinates: output (t, h, w), tap (kt, kh, kw) reads xpad[t + kt, h + kh, w + kw]
+                        if constexpr (MMA2) {
+                            // the bytes of both CTAs are counted on the leader's barrier, which only the leader arms
+                            if (crank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
 #pragma unroll
-                        for (int m = 0; m < MT; ++m)
-                            tma_load_4d(sa + m * Cfg::A_BYTES, &tmX, &full[stage], cb * BK, w0[m] + kw, h0[m] + kh, t[m] + kt);
-                        tma_load_2d(sa + MT * Cfg::A_BYTES, &tmW, &full[stage], kb * BK, n0);
+                            for (int m = 0; m < MT; ++m)
+                                tma_load_4d_2sm(sa + m * Cfg::A_BYTES, &tmX, &full[stage], cb * BK, w0[m] + kw, h0[m] + kh,
+                                                t[m] + kt);
+                            tma_load_2d_2sm(sa + MT * Cfg::A_BYTES, &tmW, &full[stage], kb * BK, n0 + crank * (BN / 2));
+                        } else {
+                            mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+                            for (int m = 0; m < MT; ++m)
+                                tma_load_4d(sa + m * Cfg::A_BYTES, &tmX, &full[stage], cb * BK, w0[m] + kw, h0[m] + kh, t[m] + kt);
+                            tma_load_2d(sa + MT * Cfg::A_BYTES, &tmW, &full[stage], kb * BK, n0);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -139,13 +174,13 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        // ===================== MMA issuer (2-SM MMA: the leader CTA issues for the pair) =====================
+        if ((!MMA2 || crank == 0) && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(MMA2 ? 2 * BM : BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int unit = unit0; unit < num_units; unit += unit_step, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait_parked(&tempty[acc], acc_phase ^ 1);
@@ -160,17 +195,21 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t bd = umma_desc_sw128(sb + k * 32, 0, 1024);
 #pragma unroll
-                        for (int m = 0; m < MT; ++m)
-                            umma_ss(d_tmem + m * BN, umma_desc_sw128(sa + m * Cfg::A_BYTES + k * 32, 0, 1024), bd, idesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                        for (int m = 0; m < MT; ++m) {
+                            const uint64_t ad = umma_desc_sw128(sa + m * Cfg::A_BYTES + k * 32, 0, 1024);
+                            if constexpr (MMA2) umma_ss_2sm(d_tmem + m * BN, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                            else umma_ss(d_tmem + m * BN, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty[stage]);
+                    if constexpr (MMA2) umma_commit_2sm_mc(&empty[stage], static_cast<uint16_t>(3));
+                    else umma_commit(&empty[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[acc]);
+                if constexpr (MMA2) umma_commit_2sm_mc(&tfull[acc], static_cast<uint16_t>(3));
+                else umma_commit(&tfull[acc]);
             }
         }
     } else if (warp >= 4 && warp < 4 + 4 * MT) {
@@ -179,11 +218,11 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const int msel = (warp - 4) >> 2;                         // which of the MT position tiles
         const int lane = threadIdx.x & 31;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int unit = unit0; unit < num_units; unit += unit_step, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int mt = (tile / n_tiles_n) * MT + msel;
-            const int n0 = (tile % n_tiles_n) * BN;
+            const int mt = ((unit / n_tiles_n) * NC + crank) * MT + msel;
+            const int n0 = (unit % n_tiles_n) * BN;
             const int r = mt % tiles_per_frame;
             const int row = wq * 32 + lane;                       // row of the tile = (tl * bh + hl) * bw + wl
             const int t = (mt / tiles_per_frame) * p.bt + row / (p.bw * p.bh);
@@ -244,15 +283,18 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            if constexpr (MMA2) mbar_arrive_leader(&tempty[acc]);
+            else mbar_arrive(&tempty[acc]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (NC > 1) cluster_sync_all();    // no CTA leaves while the leader may still free its stages
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+        if constexpr (MMA2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+        else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -288,19 +330,39 @@ int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t C, uint64_t Wp, ui
     return K5_OK;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int CL>
 int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t st) {
-    using Cfg = ConvCfg<BN, MT>;
-    static bool configured = false;
-    auto kern = conv3d_kernel<BN, MT>;
-    if (!configured) {
+    using Cfg = ConvCfg<BN, MT, CL>;
+    constexpr int NC = CL == 1 ? 1 : 2;
+    static int max_ctas = 0;            // CTAs that can be resident at once (whole clusters only when NC > 1)
+    auto kern = conv3d_kernel<BN, MT, CL>;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_ctas == 0) {
         K5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
+        max_ctas = sm_count();
+        if (NC > 1) {
+            cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / NC * NC));
+            int n_clusters = 0;
+            K5_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+            K5_REQUIRE(n_clusters > 0, "conv3d: no thread-block cluster fits this device");
+            max_ctas = n_clusters * NC;
+        }
     }
     const int mtiles = ((p.T + p.bt - 1) / p.bt) * p.tiles_w * p.tiles_h;
-    const int tiles = ((mtiles + MT - 1) / MT) * ((p.Cout + BN - 1) / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(tmX, tmW, p);
+    const int groups = (mtiles + MT - 1) / MT;
+    const int units = ((groups + NC - 1) / NC) * ((p.Cout + BN - 1) / BN) * NC;
+    cfg.gridDim = dim3(static_cast<unsigned>(units < max_ctas ? units : max_ctas));
+    K5_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p));
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }
@@ -338,10 +400,22 @@ int conv3d_causal(const bf16* xpad, int T, int H, int W, int Cin, const bf16* w,
     CUtensorMap tmX, tmW;
     K5_TRY(make_tmap_4d(&tmX, xpad, Cin, W + 2, H + 2, T + 2, bw, bh, bt));
     const int BN = (Cout_pad % 256 == 0) ? 256 : (Cout_pad % 128 == 0 ? 128 : 64);
-    K5_TRY(make_tmap_2d_bf16(&tmW, w, Cout_pad, static_cast<uint64_t>(27) * Cin, static_cast<uint64_t>(27) * Cin, BN));
-    if (BN == 256) return launch_conv<256, 1>(tmX, tmW, p, st);
-    if (BN == 128) return launch_conv<128, 2>(tmX, tmW, p, st);
-    return launch_conv<64, 2>(tmX, tmW, p, st);
+    // CTA pairs under one 2-SM MMA (K5_CONV_CLUSTER=0 restores the single-CTA kernel: tuning / A-B)
+    static int pair = -1;
+    if (pair < 0) {
+        const char* ev = getenv("K5_CONV_CLUSTER");
+        pair = ev ? (atoi(ev) != 0) : CONV_CLUSTER_DEFAULT;
+    }
+    K5_TRY(make_tmap_2d_bf16(&tmW, w, Cout_pad, static_cast<uint64_t>(27) * Cin, static_cast<uint64_t>(27) * Cin,
+                             pair ? BN / 2 : BN));
+    if (pair) {
+        if (BN == 256) return launch_conv<256, 1, 3>(tmX, tmW, p, st);
+        if (BN == 128) return launch_conv<128, 2, 3>(tmX, tmW, p, st);
+        return launch_conv<64, 2, 3>(tmX, tmW, p, st);
+    }
+    if (BN == 256) return launch_conv<256, 1, 1>(tmX, tmW, p, st);
+    if (BN == 128) return launch_conv<128, 2, 1>(tmX, tmW, p, st);
+    return launch_conv<64, 2, 1>(tmX, tmW, p, st);
 }
 
 }  // namespace k5
