@@ -220,18 +220,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int i = 0; i < 16; ++i) rope_row[i] = __ldg(rp + i);
                 }
             }
-            // Gated residual: this thread's slice of the residual row (HBM, not L2 resident) is fetched before the wait too.
-            constexpr int CPW_ = (BN / 32 + 1) / 2;
-            uint4 resid_row[EPI == EPI_GATE ? 4 * CPW_ : 1];
+            // Gated residual (HBM, not L2 resident): fetched before the wait too, in the TRANSPOSED pattern the stores
+            // use below (8 lanes cover one 128-byte line of a row; lane = (row 4i + lane / 8, 16-byte chunk lane % 8)).
+            constexpr int BPW_ = (BN / 64 + 1) / 2;          // 64-column blocks per warp set
+            uint4 resid_t[EPI == EPI_GATE ? 8 * BPW_ : 1];
             if constexpr (EPI == EPI_GATE) {
-                if (row_ok) {
 #pragma unroll
-                    for (int c = 0; c < CPW_; ++c) {
-                        const int cc = chalf * CPW_ + c;
-                        if (cc < BN / 32) {
-                            const uint4* res = reinterpret_cast<const uint4*>(e.resid + static_cast<size_t>(row) * e.ldr + n0 + cc * 32);
+                for (int c = 0; c < BPW_; ++c) {
+                    const int cc = chalf * BPW_ + c;
+                    if (cc < BN / 64) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) resid_row[4 * c + i] = res[i];
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = m0 + wq * 32 + 4 * i + (lane >> 3);
+                            if (rr < M)
+                                resid_t[8 * c + i] = *reinterpret_cast<const uint4*>(
+                                    e.resid + static_cast<size_t>(rr) * e.ldr + n0 + cc * 64 + (lane & 7) * 8);
                         }
                     }
                 }
@@ -297,29 +300,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                     }
+                    // Transpose the warp's 32 rows x 128 B through shared memory (XOR-swizzled 16-byte chunks, conflict
+                    // free) so that 8 lanes cover one 128-byte line and every store instruction writes 4 full lines
+                    // (a row-per-thread store touches 32 different lines per instruction).
+                    uint4* xw = reinterpret_cast<uint4*>(xpose + (warp - 4) * 4096);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint4 v;
+                        v.x = pack_bf16x2(x[8 * i + 0], x[8 * i + 1]);
+                        v.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
+                        v.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]);
+                        v.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
+                        xw[lane * 8 + (i ^ (lane & 7))] = v;
+                    }
+                    __syncwarp();
+                    const int chunk = lane & 7;
+                    uint4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + (lane >> 3);
+                        v[i] = xw[r * 8 + (chunk ^ (r & 7))];
+                    }
+                    __syncwarp();
                     if (e.peers.n > 0 && col0 >= e.peers.col0) {
-                        // K | V columns of a temporal shard: all-gather fused into the epilogue.  Transpose the
-                        // warp's 32 x 128 B through shared memory (XOR-swizzled 16-byte chunks, conflict free) so
-                        // that 8 lanes cover one 128-byte line, then store the lines to every rank's K|V buffer.
-                        uint4* xw = reinterpret_cast<uint4*>(xpose + (warp - 4) * 4096);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            uint4 v;
-                            v.x = pack_bf16x2(x[8 * i + 0], x[8 * i + 1]);
-                            v.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
-                            v.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]);
-                            v.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
-                            xw[lane * 8 + (i ^ (lane & 7))] = v;
-                        }
-                        __syncwarp();
-                        const int chunk = lane & 7;
-                        uint4 v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 4 * i + (lane >> 3);
-                            v[i] = xw[r * 8 + (chunk ^ (r & 7))];
-                        }
-                        __syncwarp();
+                        // K | V columns of a temporal shard: all-gather fused into the epilogue - the lines go to every
+                        // rank's K|V buffer (this rank's own included) over NVLink peer memory
                         const size_t colo = static_cast<size_t>(col0 - e.peers.col0) + chunk * 8;
                         for (int pr = 0; pr < e.peers.n; ++pr) {
                             bf16* base = e.peers.dst[pr];
@@ -330,70 +335,93 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     *reinterpret_cast<uint4*>(base + (static_cast<size_t>(e.peers.row0) + rr) * e.peers.ld + colo) = v[i];
                             }
                         }
-                    } else if (row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(e.out + static_cast<size_t>(row) * e.ldo + col0);
+                    } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            uint4 v;
-                            v.x = pack_bf16x2(x[8 * i + 0], x[8 * i + 1]);
-                            v.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
-                            v.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]);
-                            v.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
-                            dst[i] = v;
+                            const int rr = m0 + wq * 32 + 4 * i + (lane >> 3);
+                            if (rr < M)
+                                *reinterpret_cast<uint4*>(e.out + static_cast<size_t>(rr) * e.ldo + col0 + chunk * 8) = v[i];
                         }
                     }
                 }
             } else {
-                constexpr int CPW = (BN / 32 + 1) / 2;          // 32-column chunks per warp set
+                // 64 columns at a time.  The accumulator arrives with thread = row; a row-per-thread store would touch 32
+                // different 128-byte lines per instruction, so the bf16 values are transposed through the warp's
+                // shared-memory patch (XOR-swizzled 16-byte chunks, conflict free) and leave as full lines: 8 lanes
+                // per row, 4 rows per instruction.  The residual of the gated epilogue comes in the same pattern.
+                constexpr int BPW = (BN / 64 + 1) / 2;          // 64-column blocks per warp set
+                uint4* xw = reinterpret_cast<uint4*>(xpose + (warp - 4) * 4096);
+                const int chunk = lane & 7;
 #pragma unroll
-                for (int cl = 0; cl < CPW; ++cl) {
-                    const int c = chalf * CPW + cl;
-                    if (c >= BN / 32) break;
-                    uint32_t raw[32];
-                    tmem_ld32(t_row + c * 32, raw);
+                for (int cl = 0; cl < BPW; ++cl) {
+                    const int c = chalf * BPW + cl;
+                    if (c >= BN / 64) break;
+                    uint32_t raw[64];
+                    tmem_ld32(t_row + c * 64, raw);
+                    tmem_ld32(t_row + c * 64 + 32, raw + 32);
                     tmem_wait_ld();
-                    const int col0 = n0 + c * 32;
-                    if (row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(e.out + static_cast<size_t>(row) * e.ldo + col0);
+                    const int col0 = n0 + c * 64;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float y[8];
+                    for (int i = 0; i < 8; ++i) {
+                        float y[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(raw[8 * i + j]);
-                            if (e.bias) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + 2 * i);
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + 2 * i + 1);
-                                y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
-                                y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
-                            }
-                            if constexpr (EPI == EPI_GELU) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    bf16_round2(y[2 * j], y[2 * j + 1]);
-                                    y[2 * j] = gelu_erf(y[2 * j]);
-                                    y[2 * j + 1] = gelu_erf(y[2 * j + 1]);
-                                }
-                            }
-                            if constexpr (EPI == EPI_GATE) {
-                                const uint4 r = resid_row[4 * cl + i];
-                                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.gate + col0) + 2 * i);
-                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.gate + col0) + 2 * i + 1);
-                                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    bf16_round2(y[2 * j], y[2 * j + 1]);
-                                    y[2 * j] = __fadd_rn(bf16_lo(rr[j]), __fmul_rn(gg[2 * j], y[2 * j]));
-                                    y[2 * j + 1] = __fadd_rn(bf16_hi(rr[j]), __fmul_rn(gg[2 * j + 1], y[2 * j + 1]));
-                                }
-                            }
-                            uint4 o;
-                            o.x = pack_bf16x2(y[0], y[1]);
-                            o.y = pack_bf16x2(y[2], y[3]);
-                            o.z = pack_bf16x2(y[4], y[5]);
-                            o.w = pack_bf16x2(y[6], y[7]);
-                            dst[i] = o;
+                        for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(raw[8 * i + j]);
+                        if (e.bias) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + 2 * i);
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + 2 * i + 1);
+                            y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+                            y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
                         }
+                        if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                bf16_round2(y[2 * j], y[2 * j + 1]);
+                                y[2 * j] = gelu_erf(y[2 * j]);
+                                y[2 * j + 1] = gelu_erf(y[2 * j + 1]);
+                            }
+                        }
+                        uint4 v;                                  // bf16(acc + bias) / bf16(gelu(bf16(acc + bias)))
+                        v.x = pack_bf16x2(y[0], y[1]);
+                        v.y = pack_bf16x2(y[2], y[3]);
+                        v.z = pack_bf16x2(y[4], y[5]);
+                        v.w = pack_bf16x2(y[6], y[7]);
+                        xw[lane * 8 + (i ^ (lane & 7))] = v;
+                    }
+                    __syncwarp();
+                    uint4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + (lane >> 3);
+                        v[i] = xw[r * 8 + (chunk ^ (r & 7))];
+                    }
+                    __syncwarp();
+                    float gg[8];
+                    if constexpr (EPI == EPI_GATE) {
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(e.gate + col0 + chunk * 8));
+                        const float4 g1 = __ldg(reinterpret_cast<const float4*>(e.gate + col0 + chunk * 8) + 1);
+                        gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w;
+                        gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = m0 + wq * 32 + 4 * i + (lane >> 3);
+                        if (rr >= M) continue;
+                        uint4 o = v[i];
+                        if constexpr (EPI == EPI_GATE) {
+                            // x + gate * bf16(acc + bias), products and sums rounded like the reference's fp32 ops (nn.py:30-33)
+                            const uint4 r = resid_t[8 * cl + i];
+                            const uint32_t rr4[4] = {r.x, r.y, r.z, r.w};
+                            const uint32_t yy4[4] = {o.x, o.y, o.z, o.w};
+                            uint32_t oo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float lo = __fadd_rn(bf16_lo(rr4[j]), __fmul_rn(gg[2 * j], bf16_lo(yy4[j])));
+                                const float hi = __fadd_rn(bf16_hi(rr4[j]), __fmul_rn(gg[2 * j + 1], bf16_hi(yy4[j])));
+                                oo[j] = pack_bf16x2(lo, hi);
+                            }
+                            o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+                        }
+                        *reinterpret_cast<uint4*>(e.out + static_cast<size_t>(rr) * e.ldo + col0 + chunk * 8) = o;
                     }
                 }
             }
