@@ -22,66 +22,83 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 // TextEmbeddings (nn.py:70-72): bf16(LN(x) * w + b).  One warp per row, the row is held in registers
 // (D <= 2048, D % 256 == 0), two-pass statistics in fp32.
 constexpr int LN_MAXV = 8;
+constexpr int LN_BLOCKS_PER_SM = 2;     // 127 registers x 256 threads: two blocks are resident per SM
+// Persistent: a warp walks rows warp_id, warp_id + n_warps, ... and issues the loads of its NEXT row before it reduces
+// and writes the current one, so HBM reads stay in flight across the dependent reduce -> normalise -> store chain.
 __global__ void __launch_bounds__(256) ln_rows_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo,
                                                       int S, int D, const float* __restrict__ mul,
                                                       const float* __restrict__ add, int plus_one, float eps) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= S) return;
     const int lane = threadIdx.x & 31;
     const int nv = D >> 8;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
-    float v[LN_MAXV][8];
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        if (i < nv) {
-            const uint4 u = __ldg(xr + i * 32 + lane);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[i][2 * j] = bf16_lo(w[j]);
-                v[i][2 * j + 1] = bf16_hi(w[j]);
-                sum += v[i][2 * j] + v[i][2 * j + 1];
-            }
-        }
-    }
-    const float mean = warp_sum(sum) / static_cast<float>(D);
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        if (i < nv) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = v[i][j] - mean;
-                sq += d * d;
-            }
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
-    uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldo);
+    const int n_warps = gridDim.x * 8;
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= S) return;
     const float one = plus_one ? 1.0f : 0.0f;
+    uint4 nxt[LN_MAXV];
+    {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        if (i < nv) {
-            const int c0 = (i * 32 + lane) * 8;
-            const float4 m0 = __ldg(reinterpret_cast<const float4*>(mul + c0));
-            const float4 m1 = __ldg(reinterpret_cast<const float4*>(mul + c0 + 4));
-            const float4 a0 = __ldg(reinterpret_cast<const float4*>(add + c0));
-            const float4 a1 = __ldg(reinterpret_cast<const float4*>(add + c0 + 4));
-            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-            const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float y[8];
+        for (int i = 0; i < LN_MAXV; ++i)
+            if (i < nv) nxt[i] = __ldg(xr + i * 32 + lane);
+    }
+    for (; row < S; row += n_warps) {
+        float v[LN_MAXV][8];
+        float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float n = (v[i][j] - mean) * rstd;
-                y[j] = __fadd_rn(__fmul_rn(n, __fadd_rn(mm[j], one)), aa[j]);
+        for (int i = 0; i < LN_MAXV; ++i) {
+            if (i < nv) {
+                const uint32_t w[4] = {nxt[i].x, nxt[i].y, nxt[i].z, nxt[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[i][2 * j] = bf16_lo(w[j]);
+                    v[i][2 * j + 1] = bf16_hi(w[j]);
+                    sum += v[i][2 * j] + v[i][2 * j + 1];
+                }
             }
-            uint4 o;
-            o.x = pack_bf16x2(y[0], y[1]);
-            o.y = pack_bf16x2(y[2], y[3]);
-            o.z = pack_bf16x2(y[4], y[5]);
-            o.w = pack_bf16x2(y[6], y[7]);
-            orow[i * 32 + lane] = o;
+        }
+        if (row + n_warps < S) {
+            const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row + n_warps) * ldx);
+#pragma unroll
+            for (int i = 0; i < LN_MAXV; ++i)
+                if (i < nv) nxt[i] = __ldg(xr + i * 32 + lane);
+        }
+        const float mean = warp_sum(sum) / static_cast<float>(D);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            if (i < nv) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = v[i][j] - mean;
+                    sq += d * d;
+                }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+        uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldo);
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            if (i < nv) {
+                const int c0 = (i * 32 + lane) * 8;
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(mul + c0));
+                const float4 m1 = __ldg(reinterpret_cast<const float4*>(mul + c0 + 4));
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(add + c0));
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(add + c0 + 4));
+                const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float n = (v[i][j] - mean) * rstd;
+                    y[j] = __fadd_rn(__fmul_rn(n, __fadd_rn(mm[j], one)), aa[j]);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(y[0], y[1]);
+                o.y = pack_bf16x2(y[2], y[3]);
+                o.z = pack_bf16x2(y[4], y[5]);
+                o.w = pack_bf16x2(y[6], y[7]);
+                orow[i * 32 + lane] = o;
+            }
         }
     }
 }
@@ -316,7 +333,10 @@ int ln_rows(const bf16* x, int ldx, bf16* out, int ldo, int S, int D, const floa
     K5_REQUIRE(D % 256 == 0 && D <= 256 * LN_MAXV, "LayerNorm: model_dim must be a multiple of 256, <= 2048");
     K5_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0, "LayerNorm: pitches must be x8");
     if (S <= 0) return K5_OK;
-    ln_rows_kernel<<<(S + 7) / 8, 256, 0, st>>>(x, ldx, out, ldo, S, D, mul, add, plus_one ? 1 : 0, eps);
+    int blocks = (S + 7) / 8;
+    const int cap = sm_count() * LN_BLOCKS_PER_SM;
+    if (blocks > cap) blocks = cap;
+    ln_rows_kernel<<<blocks, 256, 0, st>>>(x, ldx, out, ldo, S, D, mul, add, plus_one ? 1 : 0, eps);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }

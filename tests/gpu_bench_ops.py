@@ -33,7 +33,7 @@ def main():
     torch.manual_seed(0)
     only = os.environ.get("K5_BENCH_ONLY", "")
     gemms = [(S, 3 * D, D, "heads"), (S, D, D, "gate"), (S, F, D, "gelu"), (S, D, F, "gate"), (S, D, D, "store")]
-    for (M, N, K, epi) in ([] if only == "attn" else gemms):
+    for (M, N, K, epi) in ([] if only in ("attn", "ln") else gemms):
         a = torch.randn(M, K, device=dev).bfloat16()
         w = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
@@ -51,6 +51,13 @@ def main():
     if only == "gemm":
         return
     heads = 28
+    if only == "ln":
+        x = torch.randn(S, D, device=dev).bfloat16()
+        sc, sh = torch.randn(D, device=dev), torch.randn(D, device=dev)
+        y = torch.empty_like(x)
+        ms = timeit(lambda: ops.ln_rows(x, sc, sh, out=y), iters=50)
+        print(f"ln_modulate S={S}: {ms:.4f} ms = {2 * S * D * 2 / ms / 1e6:.0f} GB/s", flush=True)
+        return
     qkv = torch.randn(S, 3 * D, device=dev).bfloat16()
     o = torch.empty(S, D, device=dev, dtype=torch.bfloat16)
     ms = timeit(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads, out=o), iters=5, warm=2)
