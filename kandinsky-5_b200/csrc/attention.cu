@@ -87,6 +87,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int n_items = n_qpairs * p.heads;
     const int nkv_dense = (p.Sk + KT - 1) / KT;
     const int kv_rem = p.Sk - (nkv_dense - 1) * KT;     // valid kv rows in the last tile (1..128)
+    // Static schedule: unit u of this CTA is item blockIdx.x + u * gridDim.x with both query tiles.  The last, partial
+    // round leaves most CTAs idle for a whole item; when it holds at most gridDim.x / 2 items (dense mode) each of them
+    // is split into its two query tiles and given to two CTAs - rows are independent, so the results do not change,
+    // and a CTA running one softmax warpgroup needs ~52 % of the time of a full item.
+    const int G = static_cast<int>(gridDim.x);
+    const int full_rounds = n_items / G, tail_items = n_items % G;
+    const bool split_tail = !SPARSE && p.split_tail && tail_items > 0 && 2 * tail_items <= G;
+    const int n_units = full_rounds + ((split_tail ? static_cast<int>(blockIdx.x) < 2 * tail_items
+                                                   : static_cast<int>(blockIdx.x) < tail_items) ? 1 : 0);
+    auto unit_item = [&](int u, int& mask) -> int {
+        if (u < full_rounds || !split_tail) {
+            mask = 3;
+            return static_cast<int>(blockIdx.x) + u * G;
+        }
+        mask = 1 << (blockIdx.x & 1);
+        return full_rounds * G + (static_cast<int>(blockIdx.x) >> 1);
+    };
 
     if (warp == 8 && elect_one()) {
         tma_prefetch_desc(&tmQ);
@@ -124,12 +141,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (elect_one()) {
                 int st = 0;
                 uint32_t ph = 0;
-                int i = 0;
-                for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+                uint32_t qi[2] = {0, 0};             // Q loads so far per query tile (a tile skips half units of the other)
+                for (int u = 0; u < n_units; ++u) {
+                    int mask;
+                    const int item = unit_item(u, mask);
                     const int h = item / n_qpairs;
                     const int q0 = (item % n_qpairs) * 2 * QT;
                     for (int a = 0; a < 2; ++a) {
-                        mbar_wait(&B->q_empty[a], (i & 1) ^ 1);
+                        if (!((mask >> a) & 1)) continue;
+                        mbar_wait(&B->q_empty[a], (qi[a] & 1) ^ 1);
+                        ++qi[a];
                         mbar_expect_tx(&B->q_full[a], TILE_BYTES);
                         tma_load_2d(sQ + a * TILE_BYTES, &tmQ, &B->q_full[a], h * HD, q0 + a * QT);
                     }
@@ -187,8 +208,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         kph ^= 1;
                     }
                 };
-                for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+                for (int u = 0; u < n_units; ++u) {
+                    int mask;
+                    const int item = unit_item(u, mask);
                     const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
+                    if (!((mask >> a) & 1)) {
+                        // half unit of the other query tile: nothing to multiply, but the K / V ring expects this
+                        // issuer's release of every stage
+                        for (int j = 0; j < nkv; ++j) {
+                            mbar_wait(&B->k_full[kst], kph);
+                            mbar_arrive(&B->k_empty[kst]);
+                            if (++kst == KV_STAGES) {
+                                kst = 0;
+                                kph ^= 1;
+                            }
+                            mbar_wait(&B->v_full[vst], vph);
+                            mbar_arrive(&B->v_empty[vst]);
+                            if (++vst == KV_STAGES) {
+                                vst = 0;
+                                vph ^= 1;
+                            }
+                        }
+                        continue;
+                    }
                     // S_a(0) = Q_a K_0^T: needs Q_a and the S buffer (drained at the last tile of the previous item)
                     mbar_wait(&B->q_full[a], i & 1);
                     if (g > 0) mbar_wait(&B->s_free[a], (g - 1) & 1);
@@ -214,6 +256,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                             vph ^= 1;
                         }
                     }
+                    ++i;                             // units this query tile took part in (phases of q_full / o_free)
                 }
             }
         }
@@ -237,7 +280,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             while (clock64() - t0 < p.stagger) {
             }
         }
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int u = 0; u < n_units; ++u) {
+            int mask;
+            const int item = unit_item(u, mask);
+            if (!((mask >> a) & 1)) continue;             // half unit of the other query tile
             const int h = item / n_qpairs;
             const int row = (item % n_qpairs) * 2 * QT + a * QT + wq * 32 + lane;
             float m_used = -INFINITY;
@@ -547,11 +593,12 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
-    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, nq4 = 2;
+    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, nq4 = 2, split_tail = 1;
     if (npoly < 0) {
         if (const char* im = getenv("K5_ATTN_IMPL")) impl = atoi(im);
         if (impl != 2 && impl != 4) impl = ATT_IMPL_DEFAULT;
         if (const char* nq = getenv("K5_ATTN_NQ")) nq4 = atoi(nq) == 3 ? 3 : 2;
+        if (const char* sp = getenv("K5_ATTN_SPLIT_TAIL")) split_tail = atoi(sp) != 0;
         const char* sg = getenv("K5_ATTN_STAGGER");
         stagger = sg ? atoi(sg) : ATT_STAGGER_DEFAULT;
         // fraction of the exponentials evaluated on the FMA pipe (pairs out of every 8); tuning knob only
@@ -574,6 +621,7 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.item_mask = nullptr;
     p.max_pairs = 0;
     p.stagger = stagger;
+    p.split_tail = split_tail;
     if (impl == 4) return attention_fwd_v4(Q, ldq, K, ldk, V, ldv, p, nq4, st, ws_in ? *ws_in : g_sparse_ws);
     const int n_qpairs = (Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * heads;

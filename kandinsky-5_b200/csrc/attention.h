@@ -17,6 +17,7 @@ struct AttnParams {
     const uint8_t* item_mask;  // [items, max_pairs] bit (qblk*2 + half): 64x64 sub-block selected
     int max_pairs;
     int stagger;           // cycles query tile 1 starts behind query tile 0 (keeps the two exp phases apart)
+    int split_tail;        // split the items of a partial last round into their two query tiles (attention.cu)
 };
 
 // Scratch of the block-sparse pre-pass (per-item KV tile lists).  Owned by the caller so that several engines of one
