@@ -593,11 +593,10 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
-    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, nq4 = 2, split_tail = 1;
+    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, split_tail = 1;
     if (npoly < 0) {
         if (const char* im = getenv("K5_ATTN_IMPL")) impl = atoi(im);
         if (impl != 2 && impl != 4) impl = ATT_IMPL_DEFAULT;
-        if (const char* nq = getenv("K5_ATTN_NQ")) nq4 = atoi(nq) == 3 ? 3 : 2;
         if (const char* sp = getenv("K5_ATTN_SPLIT_TAIL")) split_tail = atoi(sp) != 0;
         const char* sg = getenv("K5_ATTN_STAGGER");
         stagger = sg ? atoi(sg) : ATT_STAGGER_DEFAULT;
@@ -622,7 +621,7 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.max_pairs = 0;
     p.stagger = stagger;
     p.split_tail = split_tail;
-    if (impl == 4) return attention_fwd_v4(Q, ldq, K, ldk, V, ldv, p, nq4, st, ws_in ? *ws_in : g_sparse_ws);
+    if (impl == 4) return attention_fwd_v4(Q, ldq, K, ldk, V, ldv, p, st, ws_in ? *ws_in : g_sparse_ws);
     const int n_qpairs = (Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * heads;
     const int grid = n_items < sm_count() ? n_items : sm_count();

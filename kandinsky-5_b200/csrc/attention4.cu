@@ -612,10 +612,9 @@ int run4(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv,
 
 }  // namespace
 
-int attention_fwd_v4(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, AttnParams p, int nq,
-                     cudaStream_t st, AttnSparseWs& ws) {
-    (void)nq;   // 3 query tiles do not fit TMEM with double-buffered scores
-    return run4<2>(Q, ldq, K, ldk, V, ldv, p, st, ws);
+int attention_fwd_v4(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, AttnParams p, cudaStream_t st,
+                     AttnSparseWs& ws) {
+    return run4<2>(Q, ldq, K, ldk, V, ldv, p, st, ws);   // 3 query tiles do not fit TMEM with double-buffered S and P
 }
 
 }  // namespace k5

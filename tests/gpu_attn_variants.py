@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the attention kernel variants on one B200 (not a pytest file).  The variant knobs (K5_ATTN_IMPL,
-K5_ATTN_PROBE, ...) are read once per process, so every variant runs in its own subprocess: a correctness check
+K5_ATTN_SPLIT_TAIL, K5_ATTN_POLY, K5_ATTN_STAGGER) are read once per process, so every variant runs in its own subprocess: a correctness check
 against a torch fp32 restatement (dense with a ragged KV tail, cross-attention shape, block-sparse against the masked
 dense result) followed by the isolated-kernel timing at the 5 s size (S = 47 616, 28 heads).
 Usage: python tests/gpu_attn_variants.py [name=ENV1:val,ENV2:val ...]"""
@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "kandinsky-5_b200"))
 
-DEFAULT = ["v2=K5_ATTN_IMPL:2", "v3=K5_ATTN_IMPL:3,K5_ATTN_PROBE:0", "v3probe=K5_ATTN_IMPL:3,K5_ATTN_PROBE:1"]
+DEFAULT = ["v2=K5_ATTN_IMPL:2", "v2_nosplit=K5_ATTN_IMPL:2,K5_ATTN_SPLIT_TAIL:0", "v4=K5_ATTN_IMPL:4"]
 
 
 def child():
