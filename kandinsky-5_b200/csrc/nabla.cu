@@ -6,8 +6,8 @@
 //   map[i, :] = softmax_fp32( bf16(qa_i . ka_j) / sqrt(64) )
 //   sort ascending, cumulative sum, keep the entries whose cumulative mass is >= 1 - P, OR the STA mask
 //   kv_nb = number kept, kv_inds = their block ids
-// Here: one kernel pools q and k, one kernel does a whole map row per thread block (scores, softmax, bitonic
-// sort by value in shared memory, block scan, threshold, OR with STA, ordered compaction).  The map is never
+// Here: one kernel pools q and k, one kernel does a whole map row per thread block (scores, softmax, a radix search
+// for the probability of the cut entry instead of a sort, OR with STA, ordered compaction).  The map is never
 // written to HBM (the reference materialises [1,28,1464,1464] fp32 = 240 MB per layer).
 #include "nabla.h"
 #include "ptx.cuh"
@@ -17,7 +17,9 @@ namespace k5 {
 namespace {
 
 constexpr int NB_MAX = 2048;          // max 64-token blocks per sequence (131 072 tokens)
-constexpr int SEL_THREADS = 1024;
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int EPT = NB_MAX / SEL_THREADS;      // map entries per thread (entry j = tid + e * SEL_THREADS)
 
 // pooled[b, c] = bf16( mean over the 64 rows of block b of x[:, c] )
 __global__ void pool64_kernel(const bf16* __restrict__ x, int ld, int cols, bf16* __restrict__ pooled) {
@@ -31,6 +33,7 @@ __global__ void pool64_kernel(const bf16* __restrict__ x, int ld, int cols, bf16
     }
 }
 
+// Deterministic block reduction (warp tree, then the warps in order); every thread gets the result.
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -42,31 +45,42 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
     if (lane == 0) red[warp] = v;
     __syncthreads();
     float r = red[0];
-    for (int w = 1; w < (blockDim.x >> 5); ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+#pragma unroll
+    for (int w = 1; w < SEL_WARPS; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
     return r;
 }
 
-// One (head, query block) row per thread block.
+// One (head, query block) row of the map per thread block.
+//
+// The reference sorts the row ascending, takes the cumulative sum and keeps every entry from the first position whose
+// cumulative mass reaches 1 - P.  Only that cut matters, not the order, so no sort is done: with A(v) = sum of the
+// probabilities whose bit pattern is below v (non-negative floats order like their bit patterns), the probability
+// tau of the cut entry is the LARGEST pattern with A(tau) < 1 - P.  tau is built four bits at a time (eight rounds, each
+// evaluating the 15 candidates of the next hex digit with one block reduction); entries above tau are kept, entries
+// below are dropped, and of the c entries equal to tau (frequent: the scores are bf16) the first m in index order are
+// dropped - the tie order of the reference's stable sort - where m is the number of copies of tau that still fit
+// under 1 - P.  (A 2 048-wide bitonic sort + scan took 9.2 ms per layer at the 10 s size, 64 % of it in the sort.)
 __global__ void __launch_bounds__(SEL_THREADS)
 nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int nbq, int nb, int heads, float need,
                  const uint8_t* __restrict__ sta, int sta_row0, int32_t* __restrict__ kv_count,
                  int32_t* __restrict__ kv_index, float* __restrict__ density_acc) {
-    __shared__ float key[NB_MAX];
-    __shared__ uint16_t idx[NB_MAX];
-    __shared__ float scan[NB_MAX];
-    __shared__ uint8_t keep[NB_MAX];
     __shared__ float qrow[64];
-    __shared__ float red[32];
-    __shared__ int s_cut;
-    __shared__ int warp_counts[32];
+    __shared__ float red[SEL_WARPS];
+    __shared__ float cand[SEL_WARPS][16];
+    __shared__ float total[16];
+    __shared__ int warp_counts[2][SEL_WARPS];
     const int i = blockIdx.x, h = blockIdx.y;
     const int cols = heads * 64;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     if (tid < 64) qrow[tid] = __bfloat162float(qa[static_cast<size_t>(i) * cols + h * 64 + tid]);
     __syncthreads();
     // scores: bf16(q . k) / 8 kept in bf16 (the reference's matmul and division run in bf16), then fp32 softmax
+    float pv[EPT];
     float mx = -INFINITY;
-    for (int j = tid; j < NB_MAX; j += SEL_THREADS) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int j = tid + e * SEL_THREADS;
         float s = -INFINITY;
         if (j < nb) {
             const uint4* kr = reinterpret_cast<const uint4*>(ka + static_cast<size_t>(j) * cols + h * 64);
@@ -83,91 +97,111 @@ nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int n
             }
             s = bf16_round(bf16_round(acc) * 0.125f);
         }
-        key[j] = s;
+        pv[e] = s;
         mx = fmaxf(mx, s);
     }
     mx = block_reduce(mx, red, true);
     float sum = 0.f;
-    for (int j = tid; j < NB_MAX; j += SEL_THREADS) {
-        const float e = j < nb ? expf(key[j] - mx) : 0.f;
-        key[j] = e;
-        sum += e;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        pv[e] = (tid + e * SEL_THREADS < nb) ? expf(pv[e] - mx) : 0.f;
+        sum += pv[e];
     }
     sum = block_reduce(sum, red, false);
     const float inv = 1.0f / sum;
-    for (int j = tid; j < NB_MAX; j += SEL_THREADS) {
-        key[j] = j < nb ? key[j] * inv : INFINITY;       // padding sorts to the end
-        idx[j] = static_cast<uint16_t>(j);
+    uint32_t bits[EPT];                       // bit patterns of the probabilities; entries past nb never match anything
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        pv[e] *= inv;
+        bits[e] = __float_as_uint(pv[e]);
     }
-    __syncthreads();
-    // bitonic sort ascending by probability (ties by index so that the result is deterministic)
-    int n2 = 1;
-    while (n2 < nb) n2 <<= 1;
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < n2; t += SEL_THREADS) {
-                const int p = t ^ j;
-                if (p > t) {
-                    const bool up = (t & k) == 0;
-                    const float a = key[t], b = key[p];
-                    const uint16_t ia = idx[t], ib = idx[p];
-                    const bool gt = (a > b) || (a == b && ia > ib);
-                    if (gt == up) {
-                        key[t] = b;
-                        key[p] = a;
-                        idx[t] = ib;
-                        idx[p] = ia;
-                    }
-                }
+    // ---- tau: the largest pattern v with A(v) < need, one hex digit per round
+    uint32_t v = 0;
+    float a_v = 0.f;                          // A(v)
+    for (int shift = 28; shift >= 0; shift -= 4) {
+        const uint32_t hv = v >> shift;       // low digit is 0
+        float part[15];
+#pragma unroll
+        for (int d = 0; d < 15; ++d) part[d] = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            if (tid + e * SEL_THREADS < nb) {
+                const uint32_t hb = bits[e] >> shift;
+#pragma unroll
+                for (int d = 0; d < 15; ++d)
+                    if (hb < hv + d + 1) part[d] += pv[e];          // below candidate v | ((d + 1) << shift)
             }
-            __syncthreads();
+        }
+#pragma unroll
+        for (int d = 0; d < 15; ++d) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part[d] += __shfl_xor_sync(0xffffffffu, part[d], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < 15; ++d) cand[warp][d] = part[d];
+        }
+        __syncthreads();
+        if (tid < 15) {
+            float t = cand[0][tid];
+#pragma unroll
+            for (int w = 1; w < SEL_WARPS; ++w) t += cand[w][tid];
+            total[tid] = t;
+        }
+        __syncthreads();
+        int best = 0;                         // largest digit whose candidate still has A < need (A is monotone)
+#pragma unroll
+        for (int d = 0; d < 15; ++d)
+            if (total[d] < need) best = d + 1;
+        if (best > 0) {
+            v |= static_cast<uint32_t>(best) << shift;
+            a_v = total[best - 1];
         }
     }
-    // inclusive scan of the sorted probabilities (Hillis-Steele, double buffered through `scan`)
-    for (int t = tid; t < n2; t += SEL_THREADS) scan[t] = t < nb ? key[t] : 0.f;
-    __syncthreads();
-    for (int off = 1; off < n2; off <<= 1) {
-        float v[NB_MAX / SEL_THREADS];
-        int c = 0;
-        for (int t = tid; t < n2; t += SEL_THREADS, ++c) v[c] = scan[t] + (t >= off ? scan[t - off] : 0.f);
-        __syncthreads();
-        c = 0;
-        for (int t = tid; t < n2; t += SEL_THREADS, ++c) scan[t] = v[c];
-        __syncthreads();
+    // ---- ties: entries equal to tau, the first m of them in index order are dropped
+    const float tau = __uint_as_float(v);
+    int m = NB_MAX;                           // tau == 0: zero-probability entries never reach the mass
+    if (need <= 0.f) {
+        m = 0;                                // P >= 1: the reference keeps the whole row
+    } else if (tau > 0.f && v != 0x7f800000u) {
+        const double left = static_cast<double>(need) - static_cast<double>(a_v);
+        const double q = ceil(left / static_cast<double>(tau)) - 1.0;
+        m = q < 0.0 ? 0 : (q > static_cast<double>(NB_MAX) ? NB_MAX : static_cast<int>(q));
     }
-    if (tid == 0) s_cut = nb;
-    __syncthreads();
-    for (int t = tid; t < nb; t += SEL_THREADS)
-        if (scan[t] >= need && (t == 0 || scan[t - 1] < need)) atomicMin(&s_cut, t);
-    __syncthreads();
-    const int cut = s_cut;
-    for (int t = tid; t < n2; t += SEL_THREADS) keep[t] = 0;
-    __syncthreads();
-    for (int t = tid; t < nb; t += SEL_THREADS)
-        if (t >= cut) keep[idx[t]] = 1;
-    __syncthreads();
-    if (sta)
-        for (int j = tid; j < nb; j += SEL_THREADS)
-            if (sta[static_cast<size_t>(sta_row0 + i) * nb + j]) keep[j] = 1;
-    __syncthreads();
-    // ordered compaction (ascending block id)
+    // ---- keep flags, OR with the STA row, ordered compaction (ascending block id)
     int32_t* out = kv_index + (static_cast<size_t>(h) * nbq + i) * nb;
-    int base = 0;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int j0 = 0; j0 < nb; j0 += SEL_THREADS) {
-        const int j = j0 + tid;
-        const bool k1 = j < nb && keep[j];
+    const uint8_t* sta_row = sta ? sta + static_cast<size_t>(sta_row0 + i) * nb : nullptr;
+    int base = 0, tie_base = 0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int j = tid + e * SEL_THREADS;
+        if (e * SEL_THREADS >= nb) break;                          // block-uniform
+        const bool in = j < nb;
+        const bool tie = in && bits[e] == v;
+        const unsigned bal_t = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) warp_counts[0][warp] = __popc(bal_t);
+        __syncthreads();
+        int pre_t = 0, tot_t = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_WARPS; ++w) {
+            if (w < warp) pre_t += warp_counts[0][w];
+            tot_t += warp_counts[0][w];
+        }
+        const int rank = tie_base + pre_t + __popc(bal_t & ((1u << lane) - 1u));
+        tie_base += tot_t;
+        bool k1 = in && (bits[e] > v || (tie && rank >= m));
+        if (in && sta_row && sta_row[j]) k1 = true;
         const unsigned bal = __ballot_sync(0xffffffffu, k1);
-        if (lane == 0) warp_counts[warp] = __popc(bal);
+        if (lane == 0) warp_counts[1][warp] = __popc(bal);
         __syncthreads();
         int pre = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) {
-            if (w < warp) pre += warp_counts[w];
-            tot += warp_counts[w];
+#pragma unroll
+        for (int w = 0; w < SEL_WARPS; ++w) {
+            if (w < warp) pre += warp_counts[1][w];
+            tot += warp_counts[1][w];
         }
         if (k1) out[base + pre + __popc(bal & ((1u << lane) - 1u))] = j;
         base += tot;
-        __syncthreads();
     }
     if (tid == 0) {
         kv_count[static_cast<size_t>(h) * nbq + i] = base;
