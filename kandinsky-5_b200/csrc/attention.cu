@@ -26,6 +26,10 @@
 
 #include "attention.h"
 #include "common.h"
+// Spacer instructions per MUFU pair in the softmax stream (see the loop): 2 measured best (profiles/r1_attention_v3_v4.md)
+#ifndef K5_ATTN_PAD
+#define K5_ATTN_PAD 2
+#endif
 #include "ptx.cuh"
 
 namespace k5 {
@@ -365,6 +369,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 // Software-pipelined over chunks of 8 pairs: while chunk c goes through the MUFU / polynomial, the
                 // scaled arguments of chunk c+1 are formed (FFMA2) and the results of chunk c-1 are summed and packed,
                 // so no instruction waits on a MUFU result that was issued less than ~16 instructions earlier.
+#if K5_ATTN_PAD > 0
+                float pad_chain = 1.0f;
+#endif
                 uint64_t xn[8];                          // x = s * scale*log2(e) - m * scale*log2(e) of the next chunk
                 float pc[16], pp[16];                    // exp2 of the current / previous chunk
 #pragma unroll
@@ -382,6 +389,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                             } else {
                                 pc[2 * q] = ex2_v(x0);
                                 pc[2 * q + 1] = ex2_v(x1);
+#if K5_ATTN_PAD > 0
+                                // Spacers: a dependent FMA chain that does no useful work.  The denser the MUFU instructions in a
+                                // warp's stream, the fuller the MIO queue they share with tcgen05.ld/st and the mbarrier
+                                // traffic of the scheduler's other warps; removing instructions from this loop makes the
+                                // kernel SLOWER, two spacers per pair make it 1.2 % faster isolated and 0.6 % in the step.
+#pragma unroll
+                                for (int z = 0; z < K5_ATTN_PAD; ++z)
+                                    asm volatile("fma.rn.f32 %0, %0, 0f3F800001, 0f0DA24260;" : "+f"(pad_chain));
+#endif
                             }
                             if (c < 7) {
                                 const int e = 16 * (c + 1) + 2 * q;
