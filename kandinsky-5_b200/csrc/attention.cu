@@ -195,6 +195,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 uint32_t kph = 0, vph = 0;
                 uint32_t g = 0;                     // KV tiles handled so far (over all items)
                 int i = 0;
+                [[maybe_unused]] uint32_t sq = 0, sw = 0;   // block-sparse: QKs issued / s_free phases consumed
+                [[maybe_unused]] int io = 0;                // block-sparse: units in which this query tile had any KV tile
 
                 auto issue_qk = [&](bool last_of_item) {
                     mbar_wait(&B->k_full[kst], kph);
@@ -233,6 +235,66 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                 vph ^= 1;
                             }
                         }
+                        continue;
+                    }
+                    if constexpr (SPARSE) {
+                        // Block-sparse: a KV tile none of this query tile's two 64-row blocks selected is skipped
+                        // altogether - the issuer only hands its ring stages back, the softmax warpgroup does not take
+                        // part - so the tiles of the item's UNION are not all multiplied for both query tiles.  The
+                        // K cursor stays one tile ahead of the V cursor exactly as in the dense loop below.
+                        const uint8_t* masks = p.item_mask + static_cast<size_t>(item) * p.max_pairs;
+                        auto act = [&](int j) { return ((masks[j] >> (4 * a)) & 0xFu) != 0u; };
+                        mbar_wait(&B->q_full[a], i & 1);
+                        bool first = true;
+                        auto step_k = [&](int j) {
+                            if (act(j)) {
+                                if (sq > sw) {                  // the S buffer is free once the last scores were pulled
+                                    mbar_wait(&B->s_free[a], sw & 1);
+                                    ++sw;
+                                }
+                                issue_qk(false);
+                                ++sq;
+                            } else {
+                                mbar_wait(&B->k_full[kst], kph);
+                                mbar_arrive(&B->k_empty[kst]);
+                                if (++kst == KV_STAGES) {
+                                    kst = 0;
+                                    kph ^= 1;
+                                }
+                            }
+                        };
+                        step_k(0);
+                        if (nkv == 1) umma_commit(&B->q_empty[a]);      // all QKs issued: Q_a may be replaced when they are done
+                        for (int j = 0; j < nkv; ++j) {
+                            if (j + 1 < nkv) {
+                                step_k(j + 1);
+                                if (j + 2 == nkv) umma_commit(&B->q_empty[a]);
+                            }
+                            if (act(j)) {
+                                if (first) mbar_wait(&B->o_free[a], (io & 1) ^ 1);
+                                mbar_wait(&B->p_ready[a], g & 1);
+                                mbar_wait(&B->v_full[vst], vph);
+                                tc_fence_after();
+                                const uint32_t va = skv_addr + vst * 2 * TILE_BYTES + TILE_BYTES;
+#pragma unroll
+                                for (int k = 0; k < KT / 16; ++k)
+                                    umma_ts(tO, tP + k * 8, umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
+                                            (!first || k != 0) ? 1u : 0u);
+                                umma_commit(&B->pv_done[a]);
+                                umma_commit(&B->v_empty[vst]);
+                                ++g;
+                                first = false;
+                            } else {
+                                mbar_wait(&B->v_full[vst], vph);
+                                mbar_arrive(&B->v_empty[vst]);
+                            }
+                            if (++vst == KV_STAGES) {
+                                vst = 0;
+                                vph ^= 1;
+                            }
+                        }
+                        if (!first) ++io;
+                        ++i;
                         continue;
                     }
                     // S_a(0) = Q_a K_0^T: needs Q_a and the S buffer (drained at the last tile of the previous item)
@@ -296,10 +358,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
             const uint8_t* masks = SPARSE ? p.item_mask + static_cast<size_t>(item) * p.max_pairs : nullptr;
             const int qblk2 = (a * 2 + (wq >> 1)) * 2;     // bit position of this warp's 64-row query block
-            for (int j = 0; j < nkv; ++j, ++cnt) {
+            int done = 0;                                  // KV tiles this query tile has taken part in (= j when dense)
+            for (int j = 0; j < nkv; ++j) {
                 bool actL = true, actR = true;
                 if constexpr (SPARSE) {
                     const uint32_t mb = masks[j];
+                    if (((mb >> (4 * a)) & 0xFu) == 0u) continue;   // not selected by either block of this query tile
                     actL = (mb >> qblk2) & 1u;
                     actR = (mb >> (qblk2 + 1)) & 1u;
                 }
@@ -308,7 +372,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 if (SPARSE && !actL && !actR) {
                     // nothing selected for this warp's query block in this KV tile: P = 0, S is not needed
                     mbar_arrive(&B->s_free[a]);
-                    if (j > 0) {
+                    if (done > 0) {
                         mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
                         tc_fence_after();
                     }
@@ -320,6 +384,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     tmem_wait_st();
                     tc_fence_before();
                     mbar_arrive(&B->p_ready[a]);
+                    ++cnt;
+                    ++done;
                     continue;
                 }
                 uint32_t s[128];
@@ -420,14 +486,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     unpack_f32x2(add_f32x2(sum_a, sum_b), t0, t1);
                     l = l * alpha + (t0 + t1);
                 }
-                if (j > 0) {
-                    // PV_a(j-1) must have consumed the previous P (and produced the O this thread may rescale)
+                if (done > 0) {
+                    // PV_a of the previous tile must have consumed the previous P (and produced the O this thread may rescale)
                     mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
                     tc_fence_after();
                 }
                 tmem_st32(tP + 0, s);
                 tmem_st32(tP + 32, s + 32);
-                if (j > 0 && __any_sync(0xffffffffu, need)) {
+                if (done > 0 && __any_sync(0xffffffffu, need)) {
                     uint32_t o[64];
                     tmem_ld32(tO, o);
                     tmem_ld32(tO + 32, o + 32);
@@ -440,16 +506,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&B->p_ready[a]);
+                ++cnt;
+                ++done;
             }
             // ---- epilogue: O_a / l -> bf16 -> global
-            mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
-            tc_fence_after();
             uint32_t o[64];
-            tmem_ld32(tO, o);
-            tmem_ld32(tO + 32, o + 32);
-            tmem_wait_ld();
-            tc_fence_before();
-            mbar_arrive(&B->o_free[a]);
+            if (!SPARSE || done > 0) {
+                mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
+                tc_fence_after();
+                tmem_ld32(tO, o);
+                tmem_ld32(tO + 32, o + 32);
+                tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&B->o_free[a]);
+            } else {
+                // no KV tile at all for this query tile (empty block lists): zero rows, nothing was accumulated
+#pragma unroll
+                for (int c = 0; c < 64; ++c) o[c] = 0u;
+                l = 0.f;
+            }
             if (row < p.Sq) {
                 const float inv = l > 0.f ? 1.0f / l : 0.f;
                 uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.ldo + h * HD);
