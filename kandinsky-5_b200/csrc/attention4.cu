@@ -324,7 +324,7 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // satisfied) barrier checks the body is straight-line code, which is what lets the scheduler interleave.
         auto phase_pipe = [&](uint32_t (&cur)[KT], uint32_t (&nxt)[KT]) {
             uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);
-            float pc[16], pp[16];
+            float pc[16] = {}, pp[16] = {};
             auto drain = [&](int c, int q) {              // results of quarter c-1: row sum + bf16 pack in place
 #ifndef K5_V4_NOSUM
                 const uint64_t pr = pack_f32x2(pp[2 * q], pp[2 * q + 1]);
@@ -397,7 +397,7 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // One active tile without look-ahead (last tile of an item, or the next one is skipped / needs tail masking).
         auto phase_plain = [&](uint32_t (&cur)[KT]) {
             uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);
-            float pc[16], pp[16];
+            float pc[16] = {}, pp[16] = {};
 #pragma unroll
             for (int c = 0; c <= 4; ++c) {
 #pragma unroll
