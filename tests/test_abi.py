@@ -81,3 +81,18 @@ def test_reference_yaml_configs_parse_unchanged():
         assert conf.model.dit_params.model_dim == 1792
         assert conf.model.attention.type in ("flash", "nabla")
         assert list(conf.metrics.scale_factor) == [1.0, 2.0, 2.0]
+
+
+def test_build_script_compiles_every_cuda_source():
+    """build.sh names its translation units explicitly: a kernel file that is not listed would silently be missing from
+    libk5.so (and the driver's build check would still pass)."""
+    import glob
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kandinsky-5_b200", "csrc")
+    sources = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(root, "*.cu")))
+    script = open(os.path.join(root, "build.sh")).read()
+    listed = re.search(r"for f in ([^;]+); do", script).group(1).split()
+    assert sorted(listed) == sources
+    for name in sources:
+        assert f"$B/{name}.o" in script, f"{name}.o is compiled but not linked"
