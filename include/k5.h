@@ -187,6 +187,18 @@ int k5_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, i
 int k5_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq, int Sk,
                  int heads, float scale, const int32_t* kv_count, const int32_t* kv_index, void* stream);
 
+/* Same, for callers that can PROVE |q . k| * scale * log2(e) <= score_bound_log2 for every query / key pair (the DiT
+ * can: q and k are RMS-normalised per head, nn.py:246-250, so the bound follows from the two norm weight vectors).
+ * With a bound <= 60 the kernel drops the running row maximum (softmax is shift invariant); a bound of 0 or above 60
+ * selects the general kernel of k5_attention.  A WRONG bound can overflow the exponentials. */
+int k5_attention_bounded(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq,
+                         int Sk, int heads, float scale, const int32_t* kv_count, const int32_t* kv_index,
+                         float score_bound_log2, void* stream);
+
+/* Debug builds of the library (-DK5_ATTN_TRACE) only: device buffer of 2*512*4 int64 clock stamps that CTA 0 of the
+ * attention kernel fills (tools/attn_trace.py); K5_ERR_UNSUPPORTED otherwise. */
+int k5_debug_attn_trace(void* buf);
+
 /* out = bf16(LN(x) * (mul + plus_one) + add), fp32 statistics, eps; x, out bf16 [S,D]; mul, add float32 [D]. */
 int k5_ln_rows(const void* x, int ldx, void* out, int ldo, int S, int D, const float* mul, const float* add, int plus_one,
                float eps, void* stream);

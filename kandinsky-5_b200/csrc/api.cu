@@ -163,6 +163,21 @@ int k5_attention(const void* Q, int ldq, const void* K, int ldk, const void* V, 
                          static_cast<cudaStream_t>(stream));
 }
 
+int k5_attention_bounded(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq,
+                         int Sk, int heads, float scale, const int32_t* kv_count, const int32_t* kv_index,
+                         float score_bound_log2, void* stream) {
+    K5_NEED(Q);
+    K5_NEED(K);
+    K5_NEED(V);
+    K5_NEED(O);
+    count_launch(1);
+    return attention_fwd(static_cast<const bf16*>(Q), ldq, static_cast<const bf16*>(K), ldk, static_cast<const bf16*>(V),
+                         ldv, static_cast<bf16*>(O), ldo, Sq, Sk, heads, scale, kv_count, kv_index,
+                         static_cast<cudaStream_t>(stream), nullptr, score_bound_log2);
+}
+
+int k5_debug_attn_trace(void* buf) { return attention_debug_trace(static_cast<long long*>(buf)); }
+
 int k5_ln_rows(const void* x, int ldx, void* out, int ldo, int S, int D, const float* mul, const float* add, int plus_one,
                float eps, void* stream) {
     K5_NEED(x);

@@ -34,6 +34,30 @@
 
 namespace k5 {
 
+#ifdef K5_ATTN_TRACE
+// Debug build only (-DK5_ATTN_TRACE): clock64 stamps of the softmax warps 0 and 4 of CTA 0 (one per query tile, same
+// scheduler) at four points of every KV tile, [2][4][512][8] long long, set through k5_debug_attn_trace().
+__device__ long long* g_attn_trace = nullptr;
+#define K5_TRACE(k)                                                                                       \
+    do {                                                                                                  \
+        if (g_attn_trace && blockIdx.x == 0 && lane == 0 && cnt < 512)                                    \
+            g_attn_trace[((a * 4 + wq) * 512 + cnt) * 8 + (k)] = clock64();                                \
+    } while (0)
+#define K5_TRACE_V(k, v)                                                                                  \
+    do {                                                                                                  \
+        if (g_attn_trace && blockIdx.x == 0 && lane == 0 && cnt < 512)                                    \
+            g_attn_trace[((a * 4 + wq) * 512 + cnt) * 8 + (k)] = (v);                                      \
+    } while (0)
+#define K5_TRACE_ISSUER(k)                                                                                \
+    do {                                                                                                  \
+        if (g_attn_trace && blockIdx.x == 0 && g < 512) g_attn_trace[(a * 4 * 512 + g) * 8 + (k)] = clock64(); \
+    } while (0)
+#else
+#define K5_TRACE(k)
+#define K5_TRACE_V(k, v)
+#define K5_TRACE_ISSUER(k)
+#endif
+
 namespace {
 
 constexpr int QT = 128;            // query rows per tile (2 tiles per CTA item)
@@ -44,6 +68,37 @@ constexpr int KV_STAGES = 5;
 constexpr int ATT_SMEM = 2 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + 1024 + 512;
 constexpr int ATT_THREADS = 384;
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320, TM_P0 = 384, TM_P1 = 448;
+#ifndef K5_ATTN_PROBE_PAIR
+#define K5_ATTN_PROBE_PAIR 56
+#endif
+#ifndef K5_ATTN_PV_PROBE_PAIR
+#define K5_ATTN_PV_PROBE_PAIR 12
+#endif
+// Ping-pong of the two softmax warpgroups (dense BOUNDED kernel): warp w of query tile 0 and warp w of query tile 1 sit
+// on the same scheduler and share its MUFU.  Left alone they run in phase - both stream exponentials at half rate,
+// then both load / store / synchronise while the MUFU idles (ncu: 16.9 cycles per MUFU inside the stream, 400 cycles
+// per tile outside it).  Two named barriers per warp pair hold them half a tile apart: a warp may start the
+// exponentials of a tile only after its partner has passed the middle of its own current tile.
+#ifndef K5_ATTN_PINGPONG
+#define K5_ATTN_PINGPONG 0
+#endif
+// Suspend-time hints (ns) of the single-thread roles' barrier waits; 0 = plain polling.  The TMA producer runs five
+// stages ahead and is not latency critical; the issuers' waits sit on the P -> PV -> pv_done chain.
+#ifndef K5_ATTN_PROD_HINT
+#define K5_ATTN_PROD_HINT 2000
+#endif
+#ifndef K5_ATTN_ISS_HINT
+#define K5_ATTN_ISS_HINT 0
+#endif
+// BOUNDED kernel: pair (of 64) after which the first half of P is stored (needs pv_done of the previous tile)
+#ifndef K5_ATTN_HALF_AT
+#define K5_ATTN_HALF_AT 48
+#endif
+#ifndef K5_ATTN_SPLITST
+#define K5_ATTN_SPLITST 1
+#endif
+constexpr int PROBE_PAIR = K5_ATTN_PROBE_PAIR;
+constexpr int PV_PROBE_PAIR = K5_ATTN_PV_PROBE_PAIR;   // BOUNDED: pair after which pv_done of the previous tile is probed               // BOUNDED: element pair (of 64) after which s_full of the next tile is probed
 constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: P stays <= 2^8 before a rescale is forced
 
 struct Bars {
@@ -76,7 +131,17 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
 }
 
 // NPOLY of every 8 element pairs take the polynomial path, the rest the MUFU.
-template <bool SPARSE, int NPOLY>
+//
+// BOUNDED: the caller guarantees |q . k| * scale * log2(e) <= p.score_bound <= 60 for every query / key pair (the DiT
+// RMS-normalises q and k per head, nn.py:246-250, so |q| <= 8 max|w_q|, |k| <= 8 max|w_k| and the bound follows from
+// the two norm weight vectors alone).  Softmax is shift invariant and bf16 / fp32 carry the same relative precision at
+// every magnitude, so with such a bound NO running row max is needed: P = exp2(s * scale*log2e) can neither overflow
+// (P <= 2^60, row sums <= 2^77) nor underflow, and O / l is the same number.  What disappears from the softmax
+// thread's serial stream: the 64 three-input maxima per tile, the rescale decision, the O correction path (and its
+// registers), the per-tile subtraction.  The two waits that used to sit between tiles (s_full of the next scores,
+// pv_done of the previous P) are probed without blocking from inside the exponential stream, half a tile before
+// their result is needed, so their ~100-cycle round trips overlap MUFU work (profiles/r2_attention_bounded.md).
+template <bool SPARSE, int NPOLY, bool BOUNDED>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -163,10 +228,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     for (int j = 0; j < nkv; ++j) {
                         const int kv0 = (SPARSE ? pairs[j] : j) * KT;
                         uint8_t* sk = sKV + st * 2 * TILE_BYTES;
-                        mbar_wait(&B->k_empty[st], ph ^ 1);
+                        mbar_wait_lean_a<K5_ATTN_PROD_HINT>(smem_u32(&B->k_empty[st]), ph ^ 1);
                         mbar_expect_tx(&B->k_full[st], TILE_BYTES);
                         tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, kv0);
-                        mbar_wait(&B->v_empty[st], ph ^ 1);
+                        mbar_wait_lean_a<K5_ATTN_PROD_HINT>(smem_u32(&B->v_empty[st]), ph ^ 1);
                         mbar_expect_tx(&B->v_full[st], TILE_BYTES);
                         tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, kv0);
                         if (++st == KV_STAGES) {
@@ -198,14 +263,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 [[maybe_unused]] uint32_t sq = 0, sw = 0;   // block-sparse: QKs issued / s_free phases consumed
                 [[maybe_unused]] int io = 0;                // block-sparse: units in which this query tile had any KV tile
 
-                auto issue_qk = [&](bool last_of_item) {
-                    mbar_wait(&B->k_full[kst], kph);
+                // Shared-memory descriptors advance by a constant per K step (the start-address field holds addr >> 4 and
+                // never carries out of its 14 bits), so one descriptor per operand tile is built BEFORE the wait that
+                // gates the MMA and the k-th step only adds k * stride: what is left between the barrier flipping and
+                // the last tcgen05.mma is a fence and ~2 instructions per MMA (measured before: ~450 cycles from
+                // p_ready to the PV commit, tools/attn_trace.py).
+                const uint64_t qdesc0 = umma_desc_sw128(qa, 0, 1024);
+                auto wait_iss = [&](uint64_t* bar, uint32_t parity) { mbar_wait_lean_a<K5_ATTN_ISS_HINT>(smem_u32(bar), parity); };
+                auto issue_qk = [&](bool last_of_item, uint64_t* gate, uint32_t gate_parity) {
+                    wait_iss(&B->k_full[kst], kph);
+                    const uint64_t kdesc0 = umma_desc_sw128(skv_addr + kst * 2 * TILE_BYTES, 0, 1024);
+                    if (gate) wait_iss(gate, gate_parity);           // S_a free again (the scores of the tile before are in registers)
                     tc_fence_after();
-                    const uint32_t ka = skv_addr + kst * 2 * TILE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        umma_ss(tS, umma_desc_sw128(qa + k * 32, 0, 1024), umma_desc_sw128(ka + k * 32, 0, 1024), idesc_qk,
-                                k != 0 ? 1u : 0u);
+                    for (int k = 0; k < HD / 16; ++k) umma_ss(tS, qdesc0 + 2 * k, kdesc0 + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
                     umma_commit(&B->s_full[a]);
                     umma_commit(&B->k_empty[kst]);
                     if (last_of_item) umma_commit(&B->q_empty[a]);
@@ -252,7 +323,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                     mbar_wait(&B->s_free[a], sw & 1);
                                     ++sw;
                                 }
-                                issue_qk(false);
+                                issue_qk(false, nullptr, 0);
                                 ++sq;
                             } else {
                                 mbar_wait(&B->k_full[kst], kph);
@@ -298,25 +369,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         continue;
                     }
                     // S_a(0) = Q_a K_0^T: needs Q_a and the S buffer (drained at the last tile of the previous item)
-                    mbar_wait(&B->q_full[a], i & 1);
-                    if (g > 0) mbar_wait(&B->s_free[a], (g - 1) & 1);
-                    issue_qk(nkv == 1);
+                    wait_iss(&B->q_full[a], i & 1);
+                    issue_qk(nkv == 1, g > 0 ? &B->s_free[a] : nullptr, (g - 1) & 1);
                     for (int j = 0; j < nkv; ++j, ++g) {
-                        if (j + 1 < nkv) {
-                            mbar_wait(&B->s_free[a], g & 1);
-                            issue_qk(j + 2 == nkv);
-                        }
-                        if (j == 0) mbar_wait(&B->o_free[a], (i & 1) ^ 1);
-                        mbar_wait(&B->p_ready[a], g & 1);
-                        mbar_wait(&B->v_full[vst], vph);
+                        if (j + 1 < nkv) issue_qk(j + 2 == nkv, &B->s_free[a], g & 1);
+                        if (j == 0) wait_iss(&B->o_free[a], (i & 1) ^ 1);
+                        wait_iss(&B->v_full[vst], vph);              // the V tile landed long ago: not on the critical path
+                        const uint64_t vdesc0 = umma_desc_sw128(skv_addr + vst * 2 * TILE_BYTES + TILE_BYTES, 16384, 1024);
+                        wait_iss(&B->p_ready[a], g & 1);
+                        K5_TRACE_ISSUER(4);
                         tc_fence_after();
-                        const uint32_t va = skv_addr + vst * 2 * TILE_BYTES + TILE_BYTES;
 #pragma unroll
                         for (int k = 0; k < KT / 16; ++k)
-                            umma_ts(tO, tP + k * 8, umma_desc_sw128(va + k * 2048, 16384, 1024), idesc_pv,
-                                    (j != 0 || k != 0) ? 1u : 0u);
+                            umma_ts(tO, tP + k * 8, vdesc0 + 128 * k, idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
                         umma_commit(&B->pv_done[a]);
                         umma_commit(&B->v_empty[vst]);
+                        K5_TRACE_ISSUER(5);
                         if (++vst == KV_STAGES) {
                             vst = 0;
                             vph ^= 1;
@@ -339,6 +407,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float sl2 = p.scale_log2;
         const uint64_t sl2x2 = pack_f32x2(sl2, sl2);
         uint32_t cnt = 0;
+        [[maybe_unused]] uint32_t sf_ok = 0;             // BOUNDED: s_full of the next tile was already seen complete
+        [[maybe_unused]] const uint32_t bar_s_full = smem_u32(&B->s_full[a]), bar_s_free = smem_u32(&B->s_free[a]),
+                                        bar_p_ready = smem_u32(&B->p_ready[a]), bar_pv_done = smem_u32(&B->pv_done[a]);
         if (a == 1 && p.stagger > 0) {
             // The two warpgroups share the MUFU.  Started together they stay in lock-step (exp phases collide, the
             // MUFU idles while both load / reduce / store); started half a tile apart they interleave and stay so.
@@ -352,13 +423,170 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (!((mask >> a) & 1)) continue;             // half unit of the other query tile
             const int h = item / n_qpairs;
             const int row = (item % n_qpairs) * 2 * QT + a * QT + wq * 32 + lane;
-            float m_used = -INFINITY;
             float l = 0.f;
-            bool started = false;
             const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
             const uint8_t* masks = SPARSE ? p.item_mask + static_cast<size_t>(item) * p.max_pairs : nullptr;
             const int qblk2 = (a * 2 + (wq >> 1)) * 2;     // bit position of this warp's 64-row query block
             int done = 0;                                  // KV tiles this query tile has taken part in (= j when dense)
+            if constexpr (BOUNDED) {
+                uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // row sum, carried over the item
+                for (int j = 0; j < nkv; ++j) {
+                    bool actL = true, actR = true;
+                    if constexpr (SPARSE) {
+                        const uint32_t mb = masks[j];
+                        if (((mb >> (4 * a)) & 0xFu) == 0u) continue;   // not selected by either block of this query tile
+                        actL = (mb >> qblk2) & 1u;
+                        actR = (mb >> (qblk2 + 1)) & 1u;
+                    }
+                    K5_TRACE(0);
+                    if (!sf_ok) mbar_wait_a(bar_s_full, cnt & 1);
+                    sf_ok = 0;
+                    tc_fence_after();
+                    if (SPARSE && !actL && !actR) {
+                        // nothing selected for this warp's query block in this KV tile: P = 0, S is not needed
+                        mbar_arrive_a(bar_s_free);
+                        if (done > 0) {
+                            mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
+                            tc_fence_after();
+                        }
+                        uint32_t z[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) z[c] = 0u;
+                        tmem_st32(tP + 0, z);
+                        tmem_st32(tP + 32, z);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive_a(bar_p_ready);
+                        ++cnt;
+                        ++done;
+                        continue;
+                    }
+                    // One tcgen05.ld.x32 moves 4 KB per warp at ~64 B/clk: a whole 128-column score row costs ~290 cycles
+                    // before the first exponential can issue (tests/micro/pipe_rates.cu).  So only the first 32 columns
+                    // are waited for; the other three loads stay in flight under the first 16 exponential pairs.
+                    uint32_t s[128];
+                    tmem_ld32(tS + 0, s);
+                    tmem_wait_ld_regs(s);
+                    K5_TRACE(1);
+                    tmem_ld32(tS + 32, s + 32);
+                    tmem_ld32(tS + 64, s + 64);
+                    tmem_ld32(tS + 96, s + 96);
+                    uint32_t pv_ok = done > 0 ? 0u : 1u;
+                    const bool tail = !SPARSE && j == nkv - 1 && kv_rem < KT;
+                    auto mask_cols = [&](int c0, int c1) {
+                        if constexpr (SPARSE) {
+                            if (!actL) {
+#pragma unroll
+                                for (int c = c0; c < (c1 < 64 ? c1 : 64); ++c) s[c] = 0xff800000u;
+                            }
+                            if (!actR) {
+#pragma unroll
+                                for (int c = (c0 > 64 ? c0 : 64); c < c1; ++c) s[c] = 0xff800000u;
+                            }
+                        } else if (tail) {
+#pragma unroll
+                            for (int c = c0; c < c1; ++c)
+                                if (c >= kv_rem) s[c] = 0xff800000u;      // -inf
+                        }
+                    };
+                    uint32_t dep = 0, p48 = 0;
+                    auto pairs = [&](int q0, int q1) {
+#pragma unroll
+                        for (int q = q0; q < q1; ++q) {
+                            float x0, x1, p0, p1;
+                            unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1])), sl2x2),
+                                         x0, x1);
+                            if ((q & 7) < NPOLY) {
+                                exp2_poly2(x0, x1, p0, p1);
+                            } else {
+                                p0 = fast_exp2(x0);
+                                p1 = fast_exp2(x1);
+                            }
+                            const uint64_t pr = pack_f32x2(p0, p1);
+                            if (q & 1) sum_b = add_f32x2(sum_b, pr);
+                            else sum_a = add_f32x2(sum_a, pr);
+                            // P is packed in place: pair q overwrites s[q], an input of pair q / 2, so a pair may only run after
+                            // pair q / 2.  Pair 48 runs early (see below) and parks its result until pair 24 is done.
+                            if (q == 48) p48 = pack_bf16x2(p0, p1);
+                            else s[q] = pack_bf16x2(p0, p1);
+                            if (q == 16 || q == 32 || q == 48) dep |= __float_as_uint(p0);
+                            // the next scores are usually there by now; the parity is made to depend on this pair's result
+                            // (its sign bit, always 0) so that ptxas cannot hoist the probe to the head of the stream
+                            if (q == PROBE_PAIR)
+                                sf_ok = mbar_test_wait_a(bar_s_full, ((cnt + 1) & 1) + (__float_as_uint(p0) >> 31));
+                            // PV_a of the previous tile (issued when the previous P was published, ~300-800 cycles ago by
+                            // now) must have consumed that P before it is overwritten: probed here, pinned the same way
+                            if (q == PV_PROBE_PAIR && done > 0)
+                                pv_ok = mbar_test_wait_a(bar_pv_done, ((cnt - 1) & 1) + (__float_as_uint(p0) >> 31));
+                        }
+                    };
+                    mask_cols(0, 32);
+#if K5_ATTN_PINGPONG
+                    if (!SPARSE && mask == 3) {
+                        if (a == 1) named_bar_sync(1 + wq, 64);              // partner (tile 0) is past the middle of tile j
+                        else if (j > 0) named_bar_sync(5 + wq, 64);          // partner (tile 1) is past the middle of tile j-1
+                    }
+#endif
+                    pairs(0, 9);
+                    tmem_wait_ld_regs(s + 32);
+                    reg_fence32(s + 64);
+                    reg_fence32(s + 96);
+                    mask_cols(32, 128);
+                    // ptxas realises tcgen05.wait::ld only through the scoreboards of the loaded registers and was seen to
+                    // hoist the s_free arrive above it (SASS of this kernel, tools/sass_sched.py).  The arrive must not
+                    // happen before the last load has read S, so its address is made to depend on one exponential from
+                    // each of the three late chunks (sign bit of a positive number: always 0).  It comes as early as the
+                    // loads allow (9 pairs ~ 200 cycles into the stream): the sooner S is handed back, the sooner
+                    // QK(j+1) is issued and the likelier the s_full probe below finds the next scores in place.
+                    pairs(16, 17);
+                    pairs(32, 33);
+                    pairs(48, 49);
+                    tc_fence_before();
+                    mbar_arrive_a(bar_s_free + (dep >> 31));   // the tensor pipe may overwrite S_a with the next scores
+                    pairs(9, 16);
+                    pairs(17, 32);
+                    s[48] = p48;
+                    if (K5_ATTN_HALF_AT > 33) pairs(33, K5_ATTN_HALF_AT < 48 ? K5_ATTN_HALF_AT : 48);
+                    if (K5_ATTN_HALF_AT > 49) pairs(49, K5_ATTN_HALF_AT);
+                    K5_TRACE(2);
+#if K5_ATTN_PINGPONG
+                    if (!SPARSE && mask == 3) {
+                        // barrier id pinned behind pair 31 (sign bit of a positive number) so that the arrive stays in the middle
+                        const uint32_t pin = s[31] >> 31;           // packed bf16 pair of positive numbers: 0
+                        if (a == 0) named_bar_arrive(1 + wq + pin, 64);
+                        else if (j + 1 < nkv) named_bar_arrive(5 + wq + pin, 64);
+                    }
+#endif
+#if K5_ATTN_SPLITST
+                    // the first half of P (64 key columns) goes to TMEM under the second half's exponentials
+                    K5_TRACE_V(6, static_cast<long long>(pv_ok));
+                    if (!pv_ok) mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
+                    pv_ok = 1u;
+                    tc_fence_after();
+                    tmem_st32(tP + 0, s);
+                    K5_TRACE(7);
+#endif
+                    if (K5_ATTN_HALF_AT < 48) pairs(K5_ATTN_HALF_AT > 33 ? K5_ATTN_HALF_AT : 33, 48);
+                    pairs(K5_ATTN_HALF_AT > 49 ? K5_ATTN_HALF_AT : 49, 64);
+                    if (!pv_ok) mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
+                    tc_fence_after();
+#if !K5_ATTN_SPLITST
+                    tmem_st32(tP + 0, s);
+#endif
+                    tmem_st32(tP + 32, s + 32);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive_a(bar_p_ready);
+                    K5_TRACE(3);
+                    ++cnt;
+                    ++done;
+                }
+                float t0, t1;
+                unpack_f32x2(add_f32x2(sum_a, sum_b), t0, t1);
+                l = t0 + t1;
+            } else {
+            float m_used = -INFINITY;
+            bool started = false;
             for (int j = 0; j < nkv; ++j) {
                 bool actL = true, actR = true;
                 if constexpr (SPARSE) {
@@ -509,6 +737,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ++cnt;
                 ++done;
             }
+            }
             // ---- epilogue: O_a / l -> bf16 -> global
             uint32_t o[64];
             if (!SPARSE || done > 0) {
@@ -637,34 +866,37 @@ namespace {
 
 constexpr int ATT_IMPL_DEFAULT = 2;      // 2 = two 128-row query tiles x 128-row KV tiles (this file), 4 = attention4.cu
 constexpr int ATT_NPOLY_DEFAULT = 0;
+constexpr float ATT_MAX_SCORE_BOUND = 60.f;   // log2 units
 constexpr int ATT_STAGGER_DEFAULT = 0;
 
-template <bool SPARSE>
+template <bool SPARSE, bool BOUNDED>
 void launch_kernel(int npoly, int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                    const AttnParams& p, cudaStream_t st) {
     switch (npoly) {
-        case 0: attention_fwd_kernel<SPARSE, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-        case 2: attention_fwd_kernel<SPARSE, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-        case 4: attention_fwd_kernel<SPARSE, 4><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-        default: attention_fwd_kernel<SPARSE, 3><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        case 1: attention_fwd_kernel<SPARSE, 1, BOUNDED><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        case 2: attention_fwd_kernel<SPARSE, 2, BOUNDED><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        default: attention_fwd_kernel<SPARSE, 0, BOUNDED><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
     }
 }
 
-template <bool SPARSE, int NPOLY>
+template <bool SPARSE, int NPOLY, bool BOUNDED>
 int configure_one() {
-    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<SPARSE, NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ATT_SMEM));
+    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<SPARSE, NPOLY, BOUNDED>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    return K5_OK;
+}
+template <bool SPARSE, bool BOUNDED>
+int configure_set() {
+    K5_TRY((configure_one<SPARSE, 0, BOUNDED>()));
+    K5_TRY((configure_one<SPARSE, 1, BOUNDED>()));
+    K5_TRY((configure_one<SPARSE, 2, BOUNDED>()));
     return K5_OK;
 }
 int configure_kernels() {
-    K5_TRY((configure_one<false, 0>()));
-    K5_TRY((configure_one<false, 2>()));
-    K5_TRY((configure_one<false, 3>()));
-    K5_TRY((configure_one<false, 4>()));
-    K5_TRY((configure_one<true, 0>()));
-    K5_TRY((configure_one<true, 2>()));
-    K5_TRY((configure_one<true, 3>()));
-    K5_TRY((configure_one<true, 4>()));
+    K5_TRY((configure_set<false, false>()));
+    K5_TRY((configure_set<true, false>()));
+    K5_TRY((configure_set<false, true>()));
+    K5_TRY((configure_set<true, true>()));
     return K5_OK;
 }
 
@@ -672,7 +904,7 @@ int configure_kernels() {
 
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st, AttnSparseWs* ws_in) {
+                  cudaStream_t st, AttnSparseWs* ws_in, float score_bound) {
     K5_REQUIRE(Sq > 0 && Sk > 0 && heads > 0, "attention: empty problem");
     const bool sparse = kv_count != nullptr;
     K5_REQUIRE((kv_count == nullptr) == (kv_index == nullptr), "attention: kv_count and kv_index go together");
@@ -684,7 +916,7 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
-    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, split_tail = 1;
+    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, split_tail = 1, use_bounded = 1;
     if (npoly < 0) {
         if (const char* im = getenv("K5_ATTN_IMPL")) impl = atoi(im);
         if (impl != 2 && impl != 4) impl = ATT_IMPL_DEFAULT;
@@ -694,7 +926,8 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         // fraction of the exponentials evaluated on the FMA pipe (pairs out of every 8); tuning knob only
         const char* env = getenv("K5_ATTN_POLY");
         npoly = env ? atoi(env) : ATT_NPOLY_DEFAULT;
-        if (npoly != 0 && npoly != 2 && npoly != 3 && npoly != 4) npoly = ATT_NPOLY_DEFAULT;
+        if (npoly < 0 || npoly > 2) npoly = ATT_NPOLY_DEFAULT;
+        if (const char* bd = getenv("K5_ATTN_BOUNDED")) use_bounded = atoi(bd) != 0;
         K5_TRY(configure_kernels());
     }
     AttnParams p;
@@ -712,6 +945,8 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.max_pairs = 0;
     p.stagger = stagger;
     p.split_tail = split_tail;
+    // fixed-offset softmax only under a proven bound that keeps exp2 and the fp32 row sums far from overflow
+    const bool bounded = use_bounded && score_bound > 0.f && score_bound <= ATT_MAX_SCORE_BOUND;
     if (impl == 4) return attention_fwd_v4(Q, ldq, K, ldk, V, ldv, p, st, ws_in ? *ws_in : g_sparse_ws);
     const int n_qpairs = (Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * heads;
@@ -733,12 +968,25 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         p.item_pairs = ws.pairs;
         p.item_mask = ws.mask;
         p.max_pairs = max_pairs;
-        launch_kernel<true>(npoly, grid, tmQ, tmK, tmV, p, st);
+        if (bounded) launch_kernel<true, true>(npoly, grid, tmQ, tmK, tmV, p, st);
+        else launch_kernel<true, false>(npoly, grid, tmQ, tmK, tmV, p, st);
     } else {
-        launch_kernel<false>(npoly, grid, tmQ, tmK, tmV, p, st);
+        if (bounded) launch_kernel<false, true>(npoly, grid, tmQ, tmK, tmV, p, st);
+        else launch_kernel<false, false>(npoly, grid, tmQ, tmK, tmV, p, st);
     }
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
+}
+
+int attention_debug_trace(long long* buf) {
+#ifdef K5_ATTN_TRACE
+    K5_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace, &buf, sizeof(buf)));
+    return K5_OK;
+#else
+    (void)buf;
+    set_last_error("attention: built without -DK5_ATTN_TRACE");
+    return K5_ERR_UNSUPPORTED;
+#endif
 }
 
 AttnSparseWs::~AttnSparseWs() {

@@ -32,9 +32,15 @@ struct AttnSparseWs {
 
 // O[Sq, heads*64] = softmax(Q K^T * softmax_scale) V per head, head_dim 64, non-causal.
 // Q/K/V/O are row-major token matrices whose head h occupies columns [h*64, h*64+64).
+// score_bound: an upper bound on |q . k| * softmax_scale * log2(e) over all query / key pairs that the caller can
+// PROVE (0 = none known).  With a bound <= 60 the kernel runs the fixed-offset softmax (no running row max, see
+// attention.cu); without one it keeps the running max with lazy rescaling.  Both compute the same softmax.
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st, AttnSparseWs* ws = nullptr);
+                  cudaStream_t st, AttnSparseWs* ws = nullptr, float score_bound = 0.f);
+
+// Debug builds (-DK5_ATTN_TRACE) only: device buffer [2][512][4] of clock64 stamps written by CTA 0 (attention.cu).
+int attention_debug_trace(long long* buf);
 
 // Grows the pre-pass scratch to at least items x max_pairs entries.
 int ensure_sparse_ws(AttnSparseWs& w, size_t items, size_t max_pairs);

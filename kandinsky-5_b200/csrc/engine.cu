@@ -4,6 +4,7 @@
 // rowops.cu / nabla.cu on one stream.  No host synchronisation inside forward / sample.
 #include <unistd.h>
 
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <set>
@@ -62,6 +63,10 @@ struct AttnW {
     Lin kv;                // cross only: [2D, D]
     Lin o;
     float *qn = nullptr, *kn = nullptr;   // [64]
+    // Proven bound on |q . k| / 8 * log2(e) after the per-head RMSNorm (nn.py:246-250): |q| <= 8 max|w_q|,
+    // |k| <= 8 max|w_k| (RoPE is a rotation); 2 % slack for the bf16 roundings.  Lets the attention kernel drop the
+    // running row max (attention.h).  Set at finalize.
+    float score_bound = 0.f;
 };
 struct Block {
     size_t mod_off = 0;    // row offset into the concatenated modulation output
@@ -467,6 +472,26 @@ int engine_finalize(Engine* e) {
         K5_TRY(rope1d_table(e->args_text, 32, e->pos_dev + 4096, L, e->rope_t_arange, 0));
         K5_CHECK_CUDA(cudaStreamSynchronize(0));
     }
+    {
+        auto bound = [&](AttnW& a) -> int {
+            float q[64], k[64];
+            K5_CHECK_CUDA(cudaMemcpy(q, a.qn, sizeof(q), cudaMemcpyDeviceToHost));
+            K5_CHECK_CUDA(cudaMemcpy(k, a.kn, sizeof(k), cudaMemcpyDeviceToHost));
+            float mq = 0.f, mk = 0.f;
+            for (int i = 0; i < 64; ++i) {
+                mq = fmaxf(mq, fabsf(q[i]));
+                mk = fmaxf(mk, fabsf(k[i]));
+            }
+            a.score_bound = 8.f * mq * 8.f * mk * 0.125f * 1.4426950408889634f * 1.02f;
+            if (!(a.score_bound > 0.f) || !std::isfinite(a.score_bound)) a.score_bound = 0.f;   // unknown -> running max
+            return K5_OK;
+        };
+        for (Block& b : e->tblocks) K5_TRY(bound(b.self));
+        for (Block& b : e->vblocks) {
+            K5_TRY(bound(b.self));
+            K5_TRY(bound(b.cross));
+        }
+    }
     e->finalized = true;
     return K5_OK;
 }
@@ -705,7 +730,8 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
     count_launch(1);
     const bool timed = e->timing && visual && e->ev_used + 2 <= e->ev.size();
     if (timed) K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used], st));
-    K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st, &e->sparse_ws));
+    K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st, &e->sparse_ws,
+                         b.self.score_bound));
     if (timed) {
         K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used + 1], st));
         e->ev_used += 2;
@@ -734,7 +760,8 @@ int cross_attention(Engine* e, const Block& b, const bf16* text, int L, const fl
     gk.norm_cols = D;
     K5_TRY(lin_gemm(text, D, b.cross.kv, L, EPI_HEADS, gk, st));
     count_launch(1);
-    K5_TRY(attention_fwd(e->qkv, D, e->ckv, 2 * D, e->ckv + D, 2 * D, e->att, D, M, L, e->heads, 0.125f, nullptr, nullptr, st));
+    K5_TRY(attention_fwd(e->qkv, D, e->ckv, 2 * D, e->ckv + D, 2 * D, e->att, D, M, L, e->heads, 0.125f, nullptr, nullptr, st,
+                         nullptr, b.cross.score_bound));
     return out_proj_gate(e, e->att, b.cross.o, e->x, mod + 2 * D, M, st);
 }
 

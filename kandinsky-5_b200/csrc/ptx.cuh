@@ -115,6 +115,29 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Lean spin for the single-thread roles of the attention kernel (no poll counter, no trap): the whole loop is two
+// instructions, so a role that polls for a whole tile takes as few issue slots / MIO entries as possible from the
+// softmax warps on its scheduler.  HINT_NS > 0 adds a suspend-time hint (the thread may stay parked in hardware up to
+// that long between polls).
+template <uint32_t HINT_NS>
+__device__ __forceinline__ void mbar_wait_lean_a(uint32_t bar, uint32_t parity) {
+    if constexpr (HINT_NS == 0) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "K5_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+            "@!P bra K5_WAIT_%=;\n\t}\n" ::"r"(bar), "r"(parity)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "K5_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
+            "@!P bra K5_WAIT_%=;\n\t}\n" ::"r"(bar), "r"(parity), "r"(HINT_NS)
+            : "memory");
+    }
+}
+
 // Wait used by the single-thread roles (TMA producer, MMA issuers), whose waits last a whole tile: the suspend-time
 // hint keeps the thread parked in hardware instead of re-issuing the poll every ~40 cycles, so the poll loop does
 // not take issue slots from the softmax warps that share its scheduler (measured: 33 polls x 6 instructions per tile
@@ -287,6 +310,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+// tcgen05.wait::ld that also names 32 destination registers as read-write operands: every later use of r[0..31] then
+// depends on the wait in the compiler's eyes too (a plain wait has no register operands, so nothing but statement
+// order keeps arithmetic on freshly loaded registers behind it).  Used where loads of later chunks stay in flight
+// while an earlier chunk is already being consumed.
+__device__ __forceinline__ void tmem_wait_ld_regs(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
+}
+// Pure compiler-level register fence (no instruction): orders uses of r[0..31] after the preceding volatile asm.
+__device__ __forceinline__ void reg_fence32(uint32_t* r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -366,6 +400,11 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
     uint64_t r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -428,6 +467,10 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 }  // namespace k5

@@ -36,12 +36,18 @@ def linear(a, w, bias=None, epilogue="store", resid=None, gate=None, norm_w0=Non
     return out
 
 
-def attention(q, k, v, heads, scale=None, kv_count=None, kv_index=None, out=None):
-    """softmax(q k^T * scale) v per head; q [Sq, heads*64], k/v [Sk, heads*64] (views with a row pitch are fine)."""
+def attention(q, k, v, heads, scale=None, kv_count=None, kv_index=None, out=None, score_bound=None):
+    """softmax(q k^T * scale) v per head; q [Sq, heads*64], k/v [Sk, heads*64] (views with a row pitch are fine).
+    score_bound: a PROVEN bound on |q . k| * scale * log2(e) (k5_attention_bounded), None = general kernel."""
     q, k, v = _bf16(q), _bf16(k), _bf16(v)
     Sq, Sk = q.shape[0], k.shape[0]
     if out is None:
         out = torch.empty(Sq, heads * 64, device=q.device, dtype=torch.bfloat16)
+    if score_bound is not None:
+        check(lib().k5_attention_bounded(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out),
+                                         out.stride(0), Sq, Sk, heads, float(scale if scale is not None else 64 ** -0.5),
+                                         ptr(kv_count), ptr(kv_index), float(score_bound), stream_ptr()))
+        return out
     check(lib().k5_attention(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out), out.stride(0), Sq, Sk,
                              heads, float(scale if scale is not None else 64 ** -0.5), ptr(kv_count), ptr(kv_index),
                              stream_ptr()))

@@ -11,7 +11,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "kandinsky-5_b200"))
 
-DEFAULT = ["v2=K5_ATTN_IMPL:2", "v2_nosplit=K5_ATTN_IMPL:2,K5_ATTN_SPLIT_TAIL:0", "v4=K5_ATTN_IMPL:4"]
+DEFAULT = ["v2=K5_ATTN_IMPL:2", "bounded=K5_VARIANT_BOUND:1", "bounded_poly1=K5_VARIANT_BOUND:1,K5_ATTN_POLY:1",
+           "bounded_poly2=K5_VARIANT_BOUND:1,K5_ATTN_POLY:2"]
+# K5_VARIANT_BOUND=1: q and k are RMS-normalised per head (as the DiT does, nn.py:246-250) and the proven score bound
+# 8 * 8 / 8 * log2(e) * w_q * w_k is handed to k5_attention_bounded -> fixed-offset softmax kernel.
 
 
 def child():
@@ -36,29 +39,43 @@ def child():
     name = os.environ["K5_VARIANT_NAME"]
     g = torch.Generator(device="cuda").manual_seed(0)
     errs = []
+    bounded = os.environ.get("K5_VARIANT_BOUND") == "1"
+
+    def norm(x, w=1.0):
+        """per-head RMSNorm (weight w) -> every 64-column head slice has norm <= 8 w"""
+        if not bounded:
+            return x
+        x4 = x.float().reshape(x.shape[0], -1, 64)
+        x4 = x4 * torch.rsqrt(x4.pow(2).mean(-1, keepdim=True) + 1.1920929e-07) * w
+        return x4.reshape(x.shape).bfloat16()
+
+    def bound(wq=1.0, wk=1.0):
+        return 8.0 * wq * 8.0 * wk * 0.125 * 1.4426950408889634 * 1.02 if bounded else None
     for (Sq, Sk, heads) in [(64, 64, 2), (1000, 777, 3), (2304, 2304, 2), (4000, 256, 4), (3 * 384 + 5, 37, 2)]:
-        q = torch.randn(Sq, heads * 64, device="cuda", generator=g).bfloat16()
-        k = torch.randn(Sk, heads * 64, device="cuda", generator=g).bfloat16()
+        q = norm(torch.randn(Sq, heads * 64, device="cuda", generator=g).bfloat16())
+        k = norm(torch.randn(Sk, heads * 64, device="cuda", generator=g).bfloat16())
         v = torch.randn(Sk, heads * 64, device="cuda", generator=g).bfloat16()
-        out = ops.attention(q, k, v, heads)
+        out = ops.attention(q, k, v, heads, score_bound=bound())
         torch.cuda.synchronize()
         errs.append(rel(out, ref(q, k, v, heads)))
     # large logits: the lazy rescale has to fire
     q = (torch.randn(1536, 128, device="cuda", generator=g) * 6).bfloat16()
     k = (torch.randn(1536, 128, device="cuda", generator=g) * 6).bfloat16()
     v = torch.randn(1536, 128, device="cuda", generator=g).bfloat16()
-    errs.append(rel(ops.attention(q, k, v, 2), ref(q, k, v, 2)))
+    if bounded:      # norm weights 2.2: bound 57 (< 60), scores spread over +-40 in log2 units
+        q, k = norm(q, 2.2), norm(k, 2.2)
+    errs.append(rel(ops.attention(q, k, v, 2, score_bound=bound(2.2, 2.2)), ref(q, k, v, 2)))
     # block-sparse against the masked dense result
     S, heads = 1600, 2                      # 25 blocks: the last query item is partial for both kernels
     nb = S // 64
-    q = torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16()
-    k = torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16()
+    q = norm(torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16())
+    k = norm(torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16())
     v = torch.randn(S, heads * 64, device="cuda", generator=g).bfloat16()
     sel = torch.rand(heads, nb, nb, device="cuda", generator=g) < 0.3
     sel |= torch.eye(nb, device="cuda", dtype=torch.bool)[None]
     cnt = sel.sum(-1).to(torch.int32)
     idx = torch.argsort((~sel).to(torch.int8), dim=-1, stable=True).to(torch.int32)
-    out = ops.attention(q, k, v, heads, kv_count=cnt.contiguous(), kv_index=idx.contiguous())
+    out = ops.attention(q, k, v, heads, kv_count=cnt.contiguous(), kv_index=idx.contiguous(), score_bound=bound())
     full = sel.repeat_interleave(64, 1).repeat_interleave(64, 2)
     errs.append(rel(out, ref(q, k, v, heads, full)))
     ok = all(e < 8e-3 for e in errs[:5]) and errs[5] < 1e-2 and errs[6] < 8e-3
@@ -67,10 +84,12 @@ def child():
         sys.exit(1)
     S, heads, D = int(os.environ.get("K5_BENCH_S", 47616)), 28, 1792
     qkv = torch.randn(S, 3 * D, device="cuda", generator=g).bfloat16()
+    qkv[:, :D] = norm(qkv[:, :D].contiguous())
+    qkv[:, D:2 * D] = norm(qkv[:, D:2 * D].contiguous())
     o = torch.empty(S, D, device="cuda", dtype=torch.bfloat16)
 
     def run():
-        ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads, out=o)
+        ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads, out=o, score_bound=bound())
 
     for _ in range(3):
         run()
@@ -82,6 +101,11 @@ def child():
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 8
+    if os.environ.get("K5_VARIANT_SAMPLE"):
+        # sampled rows of the full-size result against torch fp32
+        rows = torch.randint(0, S, (24,), device="cuda", generator=g)
+        r = ref(qkv[rows, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], heads)
+        print(f"{name}: full-size sampled rows rel-L2 {rel(o[rows], r):.2e}", flush=True)
     print(f"{name}: attn S={S} h={heads}: {ms:.2f} ms = {4.0 * S * S * D / ms / 1e9:.0f} TFLOP/s", flush=True)
 
 

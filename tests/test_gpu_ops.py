@@ -140,6 +140,43 @@ def test_attention_large_logits_lazy_rescale():
     assert rel_l2(out, _attn_ref(q, k, v, heads)) < 1e-2
 
 
+def _rms_heads(x, w=1.0):
+    """per-head RMSNorm with a scalar weight (nn.py:246-250): every 64-column head slice gets norm <= 8 w"""
+    x4 = x.float().reshape(x.shape[0], -1, 64)
+    x4 = x4 * torch.rsqrt(x4.pow(2).mean(-1, keepdim=True) + torch.finfo(torch.float32).eps) * w
+    return x4.reshape(x.shape).to(torch.bfloat16)
+
+
+def _bound(wq=1.0, wk=1.0):
+    return 8.0 * wq * 8.0 * wk * 0.125 * math.log2(math.e) * 1.02
+
+
+@pytest.mark.parametrize("Sq,Sk,heads,wq,wk", [(256, 128, 1, 1.0, 1.0), (512, 512, 4, 1.0, 1.0), (300, 37, 3, 1.3, 0.7),
+                                               (64, 24, 28, 1.0, 1.0), (1000, 777, 2, 2.2, 2.2), (2048, 4096, 28, 1.0, 1.0),
+                                               (4000, 256, 4, 1.5, 1.5)])
+def test_attention_bounded_matches_torch_and_general_kernel(Sq, Sk, heads, wq, wk):
+    """Fixed-offset softmax (k5_attention_bounded) on RMS-normalised q / k with the bound the engine derives from the
+    norm weights: same tolerance as the general kernel against torch fp32, and the two kernels agree with each other
+    to bf16 rounding (they compute the same softmax; only the scale of P before normalisation differs)."""
+    q, k = _rms_heads(_rand((Sq, heads * 64), 30), wq), _rms_heads(_rand((Sk, heads * 64), 31), wk)
+    v = _rand((Sk, heads * 64), 32)
+    assert _bound(wq, wk) <= 60.0
+    out = _ops().attention(q, k, v, heads, score_bound=_bound(wq, wk))
+    ref = _attn_ref(q, k, v, heads)
+    assert rel_l2(out, ref) < 8e-3
+    assert float((out.float() - ref).abs().max()) < 0.05
+    gen = _ops().attention(q, k, v, heads)
+    assert rel_l2(out, gen) < 6e-3
+
+
+def test_attention_bound_above_limit_selects_general_kernel():
+    """A bound above 60 (or none) must not run the fixed-offset kernel: large logits still come out right."""
+    Sq, Sk, heads = 256, 1024, 2
+    q, k, v = _rand((Sq, heads * 64), 23, 2.0), _rand((Sk, heads * 64), 24, 3.0), _rand((Sk, heads * 64), 25)
+    out = _ops().attention(q, k, v, heads, score_bound=500.0)
+    assert rel_l2(out, _attn_ref(q, k, v, heads)) < 1e-2
+
+
 def test_attention_strided_views_of_fused_qkv():
     S, heads = 640, 4
     D = heads * 64
