@@ -65,8 +65,9 @@ constexpr int KT = 128;            // kv rows per tile
 constexpr int HD = 64;             // head dim
 constexpr int TILE_BYTES = 128 * 64 * 2;
 constexpr int KV_STAGES = 5;
-constexpr int ATT_SMEM = 2 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + 1024 + 512;
-constexpr int ATT_THREADS = 384;
+constexpr int ATT_SMEM = 2 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES + 1024 + 512 + 2048;
+constexpr int ATT_THREADS = 384;             // general kernel: 8 softmax warps + 4 role warps
+constexpr int ATT_THREADS_B = 640;           // BOUNDED kernel: 16 softmax warps (two per query row half) + 4 role warps
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320, TM_P0 = 384, TM_P1 = 448;
 #ifndef K5_ATTN_PROBE_PAIR
 #define K5_ATTN_PROBE_PAIR 56
@@ -98,7 +99,8 @@ constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 320, TM_P0 = 384
 #define K5_ATTN_SPLITST 1
 #endif
 constexpr int PROBE_PAIR = K5_ATTN_PROBE_PAIR;
-constexpr int PV_PROBE_PAIR = K5_ATTN_PV_PROBE_PAIR;   // BOUNDED: pair after which pv_done of the previous tile is probed               // BOUNDED: element pair (of 64) after which s_full of the next tile is probed
+constexpr int PV_PROBE_PAIR = K5_ATTN_PV_PROBE_PAIR;   // BOUNDED: pair (of 64) after which pv_done of the previous tile is probed
+constexpr int PROBE_PAIR16 = 28, PV_PROBE_PAIR16 = 20;   // the same for the two-threads-per-row kernel (32 pairs per thread)
 constexpr float RESCALE_THRESHOLD = 8.0f;   // in log2 units: P stays <= 2^8 before a rescale is forced
 
 struct Bars {
@@ -106,6 +108,7 @@ struct Bars {
     uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
     uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2], o_free[2];
     uint32_t tmem_slot;
+    float half_sum[2][2][128];       // BOUNDED: row sums of the two column halves, exchanged once per item
 };
 
 // exp2 of a pair on the FMA / ALU pipes: x = floor(x) + f, 2^f by a degree-3 polynomial on [0,1), the integer
@@ -141,8 +144,13 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
 // registers), the per-tile subtraction.  The two waits that used to sit between tiles (s_full of the next scores,
 // pv_done of the previous P) are probed without blocking from inside the exponential stream, half a tile before
 // their result is needed, so their ~100-cycle round trips overlap MUFU work (profiles/r2_attention_bounded.md).
-template <bool SPARSE, int NPOLY, bool BOUNDED>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// W16 (with BOUNDED): 16 softmax warps, two threads per query row (key columns 0-63 / 64-127 of every KV tile).  Without
+// a row maximum the halves of a row share nothing per tile.  Dense attention gains nothing from it (the two halves
+// wait on the same barriers, so they are not independent streams: 19.1 against 18.7 ms) but block-sparse attention does:
+// a warp then owns exactly one 64 x 64 block of the tile and skips all work for a block that is not selected
+// (5.5 / 26.3 / 47.6 ms against 6.4 / 30.4 / 57.3 at densities 0.05 / 0.14 / 0.33, profiles/r2_attention.md).
+template <bool SPARSE, int NPOLY, bool BOUNDED, bool W16 = false>
+__global__ void __launch_bounds__(W16 ? ATT_THREADS_B : ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -152,6 +160,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     Bars* B = reinterpret_cast<Bars*>(smem + 2 * TILE_BYTES + KV_STAGES * 2 * TILE_BYTES);
 
     const int warp = threadIdx.x >> 5;
+    // softmax warps 0 .. NSW-1, then producer, issuer of query tile 0, TMEM allocator, issuer of query tile 1
+    static_assert(!W16 || BOUNDED, "two threads per row need the fixed-offset softmax");
+    constexpr int NSW = W16 ? 16 : 8;
+    constexpr int W_PROD = NSW, W_ISS0 = NSW + 1, W_ALLOC = NSW + 2, W_ISS1 = NSW + 3;
+    constexpr uint32_t SM_THREADS = NSW * 16;            // softmax threads per query tile
     const int n_qpairs = (p.Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * p.heads;
     const int nkv_dense = (p.Sk + KT - 1) / KT;
@@ -174,20 +187,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         return full_rounds * G + (static_cast<int>(blockIdx.x) >> 1);
     };
 
-    if (warp == 8 && elect_one()) {
+    if (warp == W_PROD && elect_one()) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
     }
-    if (warp == 9 && elect_one()) {
+    if (warp == W_ISS0 && elect_one()) {
         for (int a = 0; a < 2; ++a) {
             mbar_init(&B->q_full[a], 1);
             mbar_init(&B->q_empty[a], 1);
             mbar_init(&B->s_full[a], 1);
-            mbar_init(&B->s_free[a], 128);
-            mbar_init(&B->p_ready[a], 128);
+            mbar_init(&B->s_free[a], SM_THREADS);
+            mbar_init(&B->p_ready[a], SM_THREADS);
             mbar_init(&B->pv_done[a], 1);
-            mbar_init(&B->o_free[a], 128);
+            mbar_init(&B->o_free[a], SM_THREADS);
         }
         for (int s = 0; s < KV_STAGES; ++s) {
             mbar_init(&B->k_full[s], 1);
@@ -197,15 +210,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         fence_barrier_init();
     }
-    if (warp == 10) tmem_alloc<512>(&B->tmem_slot);
+    if (warp == W_ALLOC) tmem_alloc<512>(&B->tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = B->tmem_slot;
 
-    if (warp >= 8) {
-        reg_dec<72>();   // pool = 384 x 168 registers: 8 warps x 216 + 4 warps x 72
-        if (warp == 8) {
+    if (warp >= NSW) {
+        // register pool: 384 x 168 = 8 warps x 216 + 4 x 72 (general), 640 x 96 = 16 warps x 104 + 4 x 64 (W16);
+        // setmaxnreg can only redistribute what the CTA was launched with - asking for more blocks forever
+        if constexpr (W16) reg_dec<64>();
+        else reg_dec<72>();
+        if (warp == W_PROD) {
             // ===================== TMA producer =====================
             if (elect_one()) {
                 int st = 0;
@@ -241,14 +257,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                 }
             }
-        } else if (warp == 9 || warp == 11) {
+        } else if (warp == W_ISS0 || warp == W_ISS1) {
             // ===================== MMA issuers: one warp per query tile =====================
             // Per query tile a the order of events is fixed:  S_a(g) pulled into registers (s_free) -> QK_a(g+1);
             // P_a(g) written (p_ready) -> PV_a(g); so each issuer simply blocks on the next event of its own tile.
             // The two issuers share only the K / V ring: a stage is released when BOTH have committed their MMA on
             // it (k_empty / v_empty are initialised with count 2).
             if (elect_one()) {
-                const int a = warp == 9 ? 0 : 1;
+                const int a = warp == W_ISS0 ? 0 : 1;
                 constexpr uint32_t idesc_qk = umma_idesc_bf16(QT, KT, 0, 0);
                 constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);
                 const uint32_t tS = tmem_base + (a == 0 ? TM_S0 : TM_S1);
@@ -396,8 +412,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
     } else {
         // ===================== softmax warpgroups =====================
-        reg_inc<216>();
-        const int a = warp >> 2;                          // query tile of this warpgroup
+        if constexpr (W16) reg_inc<104>();
+        else reg_inc<216>();
+        // general kernel: warps 0-3 / 4-7 own query tile 0 / 1, a thread owns a whole 128-column score row.
+        // BOUNDED kernel: warps 0-7 / 8-15 own query tile 0 / 1; within a tile warps 0-3 take key columns 0-63 of every
+        // KV tile and warps 4-7 columns 64-127 (two threads per query row: no row maximum means nothing to exchange per
+        // tile), so each scheduler interleaves FOUR independent exponential streams instead of two.
+        const int a = W16 ? warp >> 3 : warp >> 2;        // query tile of this warpgroup
+        [[maybe_unused]] const int hf = W16 ? (warp >> 2) & 1 : 0;       // key column half
         const int wq = warp & 3;
         const int lane = threadIdx.x & 31;
         const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
@@ -428,7 +450,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint8_t* masks = SPARSE ? p.item_mask + static_cast<size_t>(item) * p.max_pairs : nullptr;
             const int qblk2 = (a * 2 + (wq >> 1)) * 2;     // bit position of this warp's 64-row query block
             int done = 0;                                  // KV tiles this query tile has taken part in (= j when dense)
-            if constexpr (BOUNDED) {
+            if constexpr (BOUNDED && !W16) {
                 uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // row sum, carried over the item
                 for (int j = 0; j < nkv; ++j) {
                     bool actL = true, actR = true;
@@ -574,6 +596,119 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     tmem_st32(tP + 0, s);
 #endif
                     tmem_st32(tP + 32, s + 32);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive_a(bar_p_ready);
+                    K5_TRACE(3);
+                    ++cnt;
+                    ++done;
+                }
+                float t0, t1;
+                unpack_f32x2(add_f32x2(sum_a, sum_b), t0, t1);
+                l = t0 + t1;
+            } else if constexpr (BOUNDED) {
+                uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // half-row sum, carried over the item
+                const uint32_t tSh = tS + 64 * hf;                  // this thread's 64 score columns of every KV tile
+                const uint32_t tPh = tP + 32 * hf;                  // ... and their 32 packed bf16 P columns
+                for (int j = 0; j < nkv; ++j) {
+                    bool act = true;
+                    if constexpr (SPARSE) {
+                        const uint32_t mb = masks[j];
+                        if (((mb >> (4 * a)) & 0xFu) == 0u) continue;   // not selected by either block of this query tile
+                        act = (mb >> (qblk2 + hf)) & 1u;            // this warp's 64 x 64 block of the tile
+                    }
+                    K5_TRACE(0);
+                    if (!sf_ok) mbar_wait_a(bar_s_full, cnt & 1);
+                    sf_ok = 0;
+                    tc_fence_after();
+                    if (SPARSE && !act) {
+                        // block not selected: P = 0 for it, S is not needed
+                        mbar_arrive_a(bar_s_free);
+                        if (done > 0) {
+                            mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
+                            tc_fence_after();
+                        }
+                        uint32_t z[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) z[c] = 0u;
+                        tmem_st32(tPh, z);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive_a(bar_p_ready);
+                        ++cnt;
+                        ++done;
+                        continue;
+                    }
+                    // One tcgen05.ld.x32 moves 4 KB per warp at ~64 B/clk (tests/micro/pipe_rates.cu): only the first 32
+                    // columns are waited for, the second load stays in flight under the first exponentials.
+                    uint32_t s[64];
+                    tmem_ld32(tSh + 0, s);
+                    tmem_wait_ld_regs(s);
+                    K5_TRACE(1);
+                    tmem_ld32(tSh + 32, s + 32);
+                    uint32_t pv_ok = done > 0 ? 0u : 1u;
+                    const bool tail = !SPARSE && j == nkv - 1 && kv_rem < KT;
+                    auto mask_cols = [&](int c0, int c1) {
+                        if (tail) {
+#pragma unroll
+                            for (int c = c0; c < c1; ++c)
+                                if (64 * hf + c >= kv_rem) s[c] = 0xff800000u;      // -inf
+                        }
+                    };
+                    uint32_t dep = 0;
+                    auto pairs = [&](int q0, int q1) {
+#pragma unroll
+                        for (int q = q0; q < q1; ++q) {
+                            float x0, x1, p0, p1;
+                            unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(s[2 * q]), __uint_as_float(s[2 * q + 1])), sl2x2),
+                                         x0, x1);
+#ifdef K5_ATTN_NOEXP     // timing experiment only (wrong results): the softmax stream without its exponentials
+                            p0 = x0 * 0.5f;
+                            p1 = x1 * 0.5f;
+#else
+                            if ((q & 7) < NPOLY) {
+                                exp2_poly2(x0, x1, p0, p1);
+                            } else {
+                                p0 = fast_exp2(x0);
+                                p1 = fast_exp2(x1);
+                            }
+#endif
+                            const uint64_t pr = pack_f32x2(p0, p1);
+                            if (q & 1) sum_b = add_f32x2(sum_b, pr);
+                            else sum_a = add_f32x2(sum_a, pr);
+                            // P is packed in place: pair q overwrites s[q], an input of pair q / 2, so a pair may only run after
+                            // pair q / 2 (the order below: 0..8, 16, 9..15, 17..31).
+                            s[q] = pack_bf16x2(p0, p1);
+                            if (q == 16) dep = __float_as_uint(p0);
+                            // Probes are pinned behind a pair's result (its sign bit, always 0) so that ptxas cannot hoist them
+                            // to the head of the stream.  s_full: the next scores, usually there by now.  pv_done: PV_a of the
+                            // previous tile must have consumed the previous P before it is overwritten.
+                            if (q == PROBE_PAIR16)
+                                sf_ok = mbar_test_wait_a(bar_s_full, ((cnt + 1) & 1) + (__float_as_uint(p0) >> 31));
+                            if (q == PV_PROBE_PAIR16 && done > 0)
+                                pv_ok = mbar_test_wait_a(bar_pv_done, ((cnt - 1) & 1) + (__float_as_uint(p0) >> 31));
+                        }
+                    };
+                    mask_cols(0, 32);
+                    pairs(0, 9);
+                    tmem_wait_ld_regs(s + 32);
+                    mask_cols(32, 64);
+                    // ptxas realises tcgen05.wait::ld only through the scoreboards of the loaded registers and was seen to
+                    // hoist the s_free arrive above it (SASS of this kernel, tools/sass_sched.py).  The arrive must not
+                    // happen before the last load has read S, so its address is made to depend on an exponential of the
+                    // late chunk (sign bit of a positive number: always 0).  It comes as early as the loads allow: the
+                    // sooner S is handed back, the sooner QK(j+1) is issued.
+                    pairs(16, 17);
+                    tc_fence_before();
+                    mbar_arrive_a(bar_s_free + (dep >> 31));   // the tensor pipe may overwrite S_a with the next scores
+                    pairs(9, 16);
+                    pairs(17, 32);
+                    K5_TRACE(2);
+                    K5_TRACE_V(6, static_cast<long long>(pv_ok));
+                    if (!pv_ok) mbar_wait_a(bar_pv_done, (cnt - 1) & 1);
+                    tc_fence_after();
+                    tmem_st32(tPh, s);
+                    K5_TRACE(7);
                     tmem_wait_st();
                     tc_fence_before();
                     mbar_arrive_a(bar_p_ready);
@@ -739,6 +874,42 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             }
             // ---- epilogue: O_a / l -> bf16 -> global
+            if constexpr (W16) {
+                // two threads per row: exchange the half-row sums through shared memory (once per item), then each
+                // thread normalises and stores its 32 of the 64 output columns
+                const int r = wq * 32 + lane;
+                B->half_sum[a][hf][r] = l;
+                named_bar_sync(1 + a, SM_THREADS);
+                l += B->half_sum[a][hf ^ 1][r];
+                uint32_t o[32];
+                if (!SPARSE || done > 0) {
+                    mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
+                    tc_fence_after();
+                    tmem_ld32(tO + 32 * hf, o);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(&B->o_free[a]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) o[c] = 0u;
+                    l = 0.f;
+                }
+                named_bar_sync(1 + a, SM_THREADS);               // half_sum may be overwritten by the next item
+                if (row < p.Sq) {
+                    const float inv = l > 0.f ? 1.0f / l : 0.f;
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.ldo + h * HD + 32 * hf);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 v;
+                        v.x = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+                        v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+                        v.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+                        v.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+                        dst[c] = v;
+                    }
+                }
+                continue;
+            }
             uint32_t o[64];
             if (!SPARSE || done > 0) {
                 mbar_wait(&B->pv_done[a], (cnt - 1) & 1);
@@ -772,7 +943,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 10) {
+    if (warp == W_ALLOC) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -873,15 +1044,15 @@ template <bool SPARSE, bool BOUNDED>
 void launch_kernel(int npoly, int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                    const AttnParams& p, cudaStream_t st) {
     switch (npoly) {
-        case 1: attention_fwd_kernel<SPARSE, 1, BOUNDED><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-        case 2: attention_fwd_kernel<SPARSE, 2, BOUNDED><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-        default: attention_fwd_kernel<SPARSE, 0, BOUNDED><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        case 1: attention_fwd_kernel<SPARSE, 1, BOUNDED, SPARSE && BOUNDED><<<grid, SPARSE && BOUNDED ? ATT_THREADS_B : ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        case 2: attention_fwd_kernel<SPARSE, 2, BOUNDED, SPARSE && BOUNDED><<<grid, SPARSE && BOUNDED ? ATT_THREADS_B : ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+        default: attention_fwd_kernel<SPARSE, 0, BOUNDED, SPARSE && BOUNDED><<<grid, SPARSE && BOUNDED ? ATT_THREADS_B : ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
     }
 }
 
 template <bool SPARSE, int NPOLY, bool BOUNDED>
 int configure_one() {
-    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<SPARSE, NPOLY, BOUNDED>,
+    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<SPARSE, NPOLY, BOUNDED, SPARSE && BOUNDED>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     return K5_OK;
 }

@@ -120,7 +120,7 @@ def main():
             k, _, v = kv.partition(":")
             env[k] = v
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, timeout=240)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, timeout=int(os.environ.get("K5_VARIANT_TIMEOUT", 240)))
             if r.returncode != 0:
                 print(f"{name}: exit code {r.returncode}", flush=True)
         except subprocess.TimeoutExpired:
