@@ -119,7 +119,7 @@ def modulation(sd: Dict[str, Tensor], pfx: str, time_embed: Tensor) -> Tensor:
 # --------------------------------------------------------------------------- embeddings
 def time_embeddings(sd, time: Tensor, model_dim: int) -> Tensor:
     """TimeEmbeddings, nn.py:43-61 (fp32)."""
-    freqs = get_freqs(model_dim // 2)
+    freqs = get_freqs(model_dim // 2).to(time.device)
     args = torch.outer(time.float(), freqs)
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     h = F.silu(_lin32(emb, sd["time_embeddings.in_layer.weight"], sd["time_embeddings.in_layer.bias"]))
@@ -143,7 +143,7 @@ def visual_embeddings(sd, x: Tensor, patch: Sequence[int], mode: str) -> Tensor:
 
 def rope_1d(pos: Tensor, dim: int):
     """RoPE1D, nn.py:99-116 -> (cos, sin) [L, dim/2]."""
-    args = torch.outer(torch.arange(1024, dtype=F32), get_freqs(dim // 2))[pos]
+    args = torch.outer(torch.arange(1024, dtype=F32), get_freqs(dim // 2)).to(pos.device)[pos]
     return torch.cos(args), torch.sin(args)
 
 
@@ -152,7 +152,7 @@ def rope_3d(shape, pos, axes_dims, scale_factor):
     T, H, W = shape
     a = []
     for i, ad in enumerate(axes_dims):
-        tab = torch.outer(torch.arange(128, dtype=F32), get_freqs(ad // 2))
+        tab = torch.outer(torch.arange(128, dtype=F32), get_freqs(ad // 2)).to(pos[0].device)
         a.append(tab[pos[i]] / scale_factor[i])
     args = torch.cat(
         [
@@ -368,7 +368,7 @@ def model_input(img: Tensor, visual_cond: bool) -> Tensor:
     """generation_utils.py:107-114: append zero cond + zero mask channels."""
     if not visual_cond:
         return img
-    return torch.cat([img, torch.zeros_like(img), torch.zeros([*img.shape[:-1], 1], dtype=img.dtype)], dim=-1)
+    return torch.cat([img, torch.zeros_like(img), torch.zeros([*img.shape[:-1], 1], dtype=img.dtype, device=img.device)], dim=-1)
 
 
 def get_velocity(sd, cfg, x, t, text, null_text, visual_rope_pos, guidance_weight, scale_factor, sparse_params=None, mode="cuda"):
