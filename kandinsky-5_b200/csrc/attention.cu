@@ -241,8 +241,41 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                     const int nkv = SPARSE ? p.item_count[item] : nkv_dense;
                     const int32_t* pairs = SPARSE ? p.item_pairs + static_cast<size_t>(item) * p.max_pairs : nullptr;
+                    [[maybe_unused]] int slab = p.slab_first, slab_left = 0, slab_tile = 0;   // dense, overlapped gather
+                    if constexpr (!SPARSE) {
+                        if (p.n_slabs > 0 && slab < 0) {
+                            // debug order of a single engine: every query row starts at the slab that holds it, as the
+                            // rank owning that row would (slab boundaries are multiples of 256 rows here)
+                            slab = 0;
+                            while (slab + 1 < p.n_slabs && p.slab_tile0[slab + 1] * KT <= q0) ++slab;
+                        }
+                    }
+                    [[maybe_unused]] const int slab_own = slab;
                     for (int j = 0; j < nkv; ++j) {
-                        const int kv0 = (SPARSE ? pairs[j] : j) * KT;
+                        int tile = SPARSE ? pairs[j] : j;
+                        if constexpr (!SPARSE) {
+                            if (p.n_slabs > 0) {
+                                // own slab first, then the slabs in the order their owners push them (rank+1, rank+2, ...)
+                                if (slab_left == 0) {
+                                    if (j > 0) slab = slab + 1 == p.n_slabs ? 0 : slab + 1;
+                                    slab_tile = p.slab_tile0[slab];
+                                    slab_left = p.slab_tile0[slab + 1] - slab_tile;
+                                    if (p.slab_flags && slab != slab_own) {
+                                        const long long t0 = clock64();
+                                        for (;;) {
+                                            uint32_t v;
+                                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.slab_flags + slab) : "memory");
+                                            if (static_cast<int32_t>(v - p.slab_epoch) >= 0) break;
+                                            if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a peer died
+                                        }
+                                        asm volatile("fence.proxy.async;" ::: "memory");     // the TMA reads what a peer's copy wrote
+                                    }
+                                }
+                                tile = slab_tile++;
+                                --slab_left;
+                            }
+                        }
+                        const int kv0 = tile * KT;
                         uint8_t* sk = sKV + st * 2 * TILE_BYTES;
                         mbar_wait_lean_a<K5_ATTN_PROD_HINT>(smem_u32(&B->k_empty[st]), ph ^ 1);
                         mbar_expect_tx(&B->k_full[st], TILE_BYTES);
@@ -285,7 +318,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 // the last tcgen05.mma is a fence and ~2 instructions per MMA (measured before: ~450 cycles from
                 // p_ready to the PV commit, tools/attn_trace.py).
                 const uint64_t qdesc0 = umma_desc_sw128(qa, 0, 1024);
+#ifdef K5_ATTN_ISS_SLEEP
+                auto wait_iss = [&](uint64_t* bar, uint32_t parity) { mbar_wait_sleep_a<K5_ATTN_ISS_SLEEP>(smem_u32(bar), parity); };
+#else
                 auto wait_iss = [&](uint64_t* bar, uint32_t parity) { mbar_wait_lean_a<K5_ATTN_ISS_HINT>(smem_u32(bar), parity); };
+#endif
                 auto issue_qk = [&](bool last_of_item, uint64_t* gate, uint32_t gate_parity) {
                     wait_iss(&B->k_full[kst], kph);
                     const uint64_t kdesc0 = umma_desc_sw128(skv_addr + kst * 2 * TILE_BYTES, 0, 1024);
@@ -1075,7 +1112,7 @@ int configure_kernels() {
 
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st, AttnSparseWs* ws_in, float score_bound) {
+                  cudaStream_t st, AttnSparseWs* ws_in, float score_bound, const AttnSlabs* slabs) {
     K5_REQUIRE(Sq > 0 && Sk > 0 && heads > 0, "attention: empty problem");
     const bool sparse = kv_count != nullptr;
     K5_REQUIRE((kv_count == nullptr) == (kv_index == nullptr), "attention: kv_count and kv_index go together");
@@ -1088,6 +1125,17 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
     static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, split_tail = 1, use_bounded = 1;
+    static std::mutex knob_mutex;
+    static PerDevice<int> configured;
+    {
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lk(configured.m);
+        if (!configured.set[dev]) {
+            K5_TRY(configure_kernels());
+            configured.set[dev] = true;
+        }
+    }
+    std::lock_guard<std::mutex> knob_lock(knob_mutex);
     if (npoly < 0) {
         if (const char* im = getenv("K5_ATTN_IMPL")) impl = atoi(im);
         if (impl != 2 && impl != 4) impl = ATT_IMPL_DEFAULT;
@@ -1099,7 +1147,6 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         npoly = env ? atoi(env) : ATT_NPOLY_DEFAULT;
         if (npoly < 0 || npoly > 2) npoly = ATT_NPOLY_DEFAULT;
         if (const char* bd = getenv("K5_ATTN_BOUNDED")) use_bounded = atoi(bd) != 0;
-        K5_TRY(configure_kernels());
     }
     AttnParams p;
     p.Sq = Sq;
@@ -1116,6 +1163,29 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.max_pairs = 0;
     p.stagger = stagger;
     p.split_tail = split_tail;
+    p.slab_flags = nullptr;
+    p.slab_epoch = 0;
+    p.n_slabs = 0;
+    p.slab_first = 0;
+    for (int& t : p.slab_tile0) t = 0;
+    if (slabs && slabs->n > 0) {     // flags == nullptr: the slab ORDER only (debug: single engine in a rank's order)
+        K5_REQUIRE(!sparse && impl == 2, "attention: the overlapped gather is implemented for the dense kernel");
+        K5_REQUIRE(slabs->n >= 1 && slabs->n <= 8 && slabs->first >= -1 && slabs->first < slabs->n && Sk % KT == 0 &&
+                       (slabs->first >= 0 || slabs->flags == nullptr) &&
+                       slabs->row0[0] == 0 && slabs->row0[slabs->n] == Sk,
+                   "attention: bad slab schedule");
+        for (int i = 0; i <= slabs->n; ++i) {
+            K5_REQUIRE(slabs->row0[i] % KT == 0 && (i == 0 || slabs->row0[i] > slabs->row0[i - 1]),
+                       "attention: slab boundaries must be increasing multiples of 128 rows");
+            K5_REQUIRE(slabs->first >= 0 || slabs->row0[i] % (2 * QT) == 0 || i == slabs->n,
+                       "attention: the per-row debug order needs slab boundaries at multiples of 256 rows");
+            p.slab_tile0[i] = slabs->row0[i] / KT;
+        }
+        p.slab_flags = slabs->flags;
+        p.slab_epoch = slabs->epoch;
+        p.n_slabs = slabs->n;
+        p.slab_first = slabs->first;
+    }
     // fixed-offset softmax only under a proven bound that keeps exp2 and the fp32 row sums far from overflow
     const bool bounded = use_bounded && score_bound > 0.f && score_bound <= ATT_MAX_SCORE_BOUND;
     if (impl == 4) return attention_fwd_v4(Q, ldq, K, ldk, V, ldv, p, st, ws_in ? *ws_in : g_sparse_ws);

@@ -16,6 +16,14 @@ struct AttnParams {
     const int32_t* item_pairs; // [items, max_pairs] KV tile ids (ascending)
     const uint8_t* item_mask;  // [items, max_pairs] bit (qblk*2 + half): 64x64 sub-block selected
     int max_pairs;
+    // Temporal shard with an overlapped all-gather (engine.cu): K | V rows arrive slab by slab (one slab per source rank)
+    // while the kernel runs.  The TMA producer walks the slabs starting at the rank's own one and, before the first
+    // tile of a foreign slab, waits until slab_flags[slab] >= slab_epoch (written by the source rank after its copy).
+    const uint32_t* slab_flags;   // null = everything is in place (no waiting)
+
+    uint32_t slab_epoch;
+    int n_slabs, slab_first;      // n_slabs == 0: natural tile order
+    int slab_tile0[9];            // first 128-row KV tile of each slab; slab_tile0[n_slabs] = number of KV tiles
     int stagger;           // cycles query tile 1 starts behind query tile 0 (keeps the two exp phases apart)
     int split_tail;        // split the items of a partial last round into their two query tiles (attention.cu)
 };
@@ -31,13 +39,21 @@ struct AttnSparseWs {
 };
 
 // O[Sq, heads*64] = softmax(Q K^T * softmax_scale) V per head, head_dim 64, non-causal.
+// Arrival schedule of the K | V rows for the overlapped all-gather of the temporal shard (see AttnParams).
+struct AttnSlabs {
+    const uint32_t* flags = nullptr;
+    uint32_t epoch = 0;
+    int n = 0, first = 0;         // first = -1 (debug, flags == nullptr): every query row starts at the slab holding it
+    int row0[9] = {};             // first row of each slab (multiples of 128); row0[n] = Sk
+};
+
 // Q/K/V/O are row-major token matrices whose head h occupies columns [h*64, h*64+64).
 // score_bound: an upper bound on |q . k| * softmax_scale * log2(e) over all query / key pairs that the caller can
 // PROVE (0 = none known).  With a bound <= 60 the kernel runs the fixed-offset softmax (no running row max, see
 // attention.cu); without one it keeps the running max with lazy rescaling.  Both compute the same softmax.
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st, AttnSparseWs* ws = nullptr, float score_bound = 0.f);
+                  cudaStream_t st, AttnSparseWs* ws = nullptr, float score_bound = 0.f, const AttnSlabs* slabs = nullptr);
 
 // Debug builds (-DK5_ATTN_TRACE) only: device buffer [2][512][4] of clock64 stamps written by CTA 0 (attention.cu).
 int attention_debug_trace(long long* buf);

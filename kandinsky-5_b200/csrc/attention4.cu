@@ -573,11 +573,15 @@ build_items4_kernel(const int32_t* __restrict__ kv_count, const int32_t* __restr
 
 template <bool SPARSE, int NQ>
 int launch4(int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        K5_CHECK_CUDA(cudaFuncSetAttribute(attention4_kernel<SPARSE, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<NQ>::SMEM));
-        configured = true;
+    static PerDevice<int> pd;
+    {
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lk(pd.m);
+        if (!pd.set[dev]) {
+            K5_CHECK_CUDA(cudaFuncSetAttribute(attention4_kernel<SPARSE, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               Cfg<NQ>::SMEM));
+            pd.set[dev] = true;
+        }
     }
     attention4_kernel<SPARSE, NQ><<<grid, Cfg<NQ>::THREADS, Cfg<NQ>::SMEM, st>>>(tmQ, tmK, tmV, p);
     return K5_OK;

@@ -28,6 +28,39 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Stream-ordered 32-bit memory operations (cuStreamWriteValue32 / cuStreamWaitValue32): executed by the stream's
+// front end, so they make progress while persistent kernels hold every SM - which a one-thread signalling kernel
+// launched on a second stream does not (the temporal shard's overlapped all-gather depends on it).
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamValueFn get_stream_fn(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<StreamValueFn>(p);
+    return nullptr;
+}
+int stream_write_u32(cudaStream_t st, uint32_t* addr, uint32_t value) {
+    static StreamValueFn fn = get_stream_fn("cuStreamWriteValue32");
+    K5_REQUIRE(fn != nullptr, "cuStreamWriteValue32 entry point not available");
+    const CUresult r = fn(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuStreamWriteValue32 failed with CUresult " + std::to_string(static_cast<int>(r)));
+        return K5_ERR_CUDA;
+    }
+    return K5_OK;
+}
+int stream_wait_geq_u32(cudaStream_t st, const uint32_t* addr, uint32_t value) {
+    static StreamValueFn fn = get_stream_fn("cuStreamWaitValue32");
+    K5_REQUIRE(fn != nullptr, "cuStreamWaitValue32 entry point not available");
+    const CUresult r = fn(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(const_cast<uint32_t*>(addr)), value,
+                          CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuStreamWaitValue32 failed with CUresult " + std::to_string(static_cast<int>(r)));
+        return K5_ERR_CUDA;
+    }
+    return K5_OK;
+}
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
@@ -51,14 +84,23 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return K5_OK;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < K5_MAX_DEVICES ? dev : K5_MAX_DEVICES - 1;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    static PerDevice<int> pd;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lk(pd.m);
+    if (!pd.set[dev]) {
+        int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        pd.v[dev] = n;
+        pd.set[dev] = true;
     }
-    return n;
+    return pd.v[dev];
 }
 
 }  // namespace k5

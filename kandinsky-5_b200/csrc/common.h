@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 #include "../../include/k5.h"
@@ -46,6 +47,20 @@ const char* get_last_error();
 // Out-of-bounds elements read as zero.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-int sm_count();
+// Per-device state.  cudaFuncSetAttribute, the cluster occupancy and the SM count belong to a DEVICE, and one process
+// may drive several (the pipeline's device_map puts the DiT and the VAE on different GPUs, kandinsky/utils.py:23-34),
+// so every "configure once" in the launchers is keyed by the current device and guarded by a mutex.
+constexpr int K5_MAX_DEVICES = 64;
+int current_device();               // cudaGetDevice, clamped to [0, K5_MAX_DEVICES)
+template <typename T>
+struct PerDevice {
+    std::mutex m;
+    bool set[K5_MAX_DEVICES] = {};
+    T v[K5_MAX_DEVICES] = {};
+};
+int sm_count();                     // of the current device
+// cuStreamWriteValue32 / cuStreamWaitValue32 (>=, wrap-safe 32-bit compare) on `st`; addr may be peer-mapped memory
+int stream_write_u32(cudaStream_t st, uint32_t* addr, uint32_t value);
+int stream_wait_geq_u32(cudaStream_t st, const uint32_t* addr, uint32_t value);
 
 }  // namespace k5

@@ -334,8 +334,11 @@ template <int BN, int MT, int CL>
 int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t st) {
     using Cfg = ConvCfg<BN, MT, CL>;
     constexpr int NC = CL == 1 ? 1 : 2;
-    static int max_ctas = 0;            // CTAs that can be resident at once (whole clusters only when NC > 1)
+    static PerDevice<int> pd;           // CTAs that can be resident at once (whole clusters only when NC > 1), per device
     auto kern = conv3d_kernel<BN, MT, CL>;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lk(pd.m);
+    int& max_ctas = pd.v[dev];
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -347,7 +350,7 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (max_ctas == 0) {
+    if (!pd.set[dev]) {
         K5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         max_ctas = sm_count();
         if (NC > 1) {
@@ -357,6 +360,7 @@ int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams
             K5_REQUIRE(n_clusters > 0, "conv3d: no thread-block cluster fits this device");
             max_ctas = n_clusters * NC;
         }
+        pd.set[dev] = true;
     }
     const int mtiles = ((p.T + p.bt - 1) / p.bt) * p.tiles_w * p.tiles_h;
     const int groups = (mtiles + MT - 1) / MT;

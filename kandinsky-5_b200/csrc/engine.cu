@@ -53,6 +53,10 @@ __global__ void dist_barrier_kernel(PeerFlags peers, uint32_t* mine, int rank, i
     }
 }
 
+// Overlapped all-gather (cross-process shards): flag slots inside each rank's 1 KB flag area.
+constexpr int FLAG_READY = 16;      // + buf * 8 + source rank: "my slab of this epoch is in your K|V buffer `buf`"
+constexpr int FLAG_DONE = 32;       // + source rank: "my attention of this epoch has finished reading"
+
 struct Lin {
     bf16* W = nullptr;     // [out, ld] bf16
     float* b = nullptr;    // [out] fp32 (bf16-rounded) or null
@@ -143,8 +147,19 @@ struct Engine {
         std::vector<void*> opened;
         uint32_t epoch = 0;
         int buf = 0;
+        // overlapped all-gather (ranks in different processes): the projection writes the local slab only, copy
+        // engines push it to the peers on `copy_st` while the attention kernel already runs on the local slab
+        bool overlap = false;
+        cudaStream_t copy_st = nullptr;
+        cudaEvent_t ev_kv = nullptr;
+        cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // the pushes out of kv[buf] have read their source
+        bool copied_valid[2] = {false, false};
     } dist;
     int f0 = 0, Tl = 0, tok0 = 0, Sl = 0;
+    // test hook (K5_DEBUG_KV_ORDER=<world>, read at set_grid): a single engine walks the KV tiles of the dense visual
+    // attention, for every query row, in the slab order the rank owning that row in a `world`-rank shard with the
+    // overlapped all-gather uses - so the whole latent can be compared BIT FOR BIT (tests/gpu_shard_ranks.py)
+    int dbg_world = 0;
 
     // grid
     int T = 0, Hp = 0, Wp = 0, S = 0, fractal = 0;
@@ -167,6 +182,10 @@ struct Engine {
         return K5_OK;
     }
     ~Engine() {
+        if (dist.copy_st) cudaStreamDestroy(dist.copy_st);
+        if (dist.ev_kv) cudaEventDestroy(dist.ev_kv);
+        for (cudaEvent_t ev : dist.ev_copied)
+            if (ev) cudaEventDestroy(ev);
         for (void* p : dist.opened) cudaIpcCloseMemHandle(p);
         if (dist.block) cudaFree(dist.block);
         for (auto& v : ev) cudaEventDestroy(v);
@@ -532,6 +551,11 @@ int engine_set_grid(Engine* e, int T, int H, int W, const int32_t* pt, const int
     }
     e->tok0 = e->f0 * Hp * Wp;
     e->Sl = e->Tl * Hp * Wp;
+    e->dbg_world = 0;
+    if (const char* ko = getenv("K5_DEBUG_KV_ORDER")) {
+        const int w = atoi(ko);
+        if (!e->dist.on && w > 1 && w <= MAX_PEERS && T >= w) e->dbg_world = w;
+    }
     e->grid_set = true;
     return K5_OK;
 }
@@ -603,6 +627,18 @@ int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
     e->dist.rank = rank;
     e->dist.world = world;
     e->dist.on = world > 1;
+    // Peers of the same process (the single-GPU tests drive several engines on one device) keep the scatter + barrier
+    // form: an attention kernel that waits for a slab inside its producer would occupy the SMs its peer needs.
+    bool cross = world > 1;
+    for (int p = 0; p < world; ++p)
+        if (p != rank && hs[p].pid == static_cast<int64_t>(getpid())) cross = false;
+    if (const char* ov = getenv("K5_DIST_OVERLAP")) cross = cross && atoi(ov) != 0;
+    e->dist.overlap = cross;
+    if (cross && !e->dist.copy_st) {
+        K5_CHECK_CUDA(cudaStreamCreateWithFlags(&e->dist.copy_st, cudaStreamNonBlocking));
+        K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->dist.ev_kv, cudaEventDisableTiming));
+        for (cudaEvent_t& ev : e->dist.ev_copied) K5_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     e->dist.epoch = 0;
     e->dist.buf = 0;
     e->grid_set = false;            // the local slab depends on (rank, world)
@@ -701,23 +737,69 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
     g.rope = rope;
     const bf16 *kp = qkv + D, *vp = qkv + 2 * D;
     int ldkv = 3 * D, Sk = M;
+    const bool overlap = shard && e->dist.overlap && !sp && e->S % 128 == 0 && (e->Hp * e->Wp) % 128 == 0;
+    AttnSlabs slabs;
+    int buf = 0;
     if (shard) {
-        // all-gather fused into the projection: the K | V columns of this rank's rows go straight from the GEMM
-        // epilogue into every rank's [S, 2D] buffer over NVLink; one flag barrier, then attention over all of S
-        const int buf = e->dist.buf;
+        buf = e->dist.buf;
         e->dist.buf ^= 1;          // the other buffer may still be read by a slower rank's previous block
-        g.peers.n = e->dist.world;
-        for (int p = 0; p < e->dist.world; ++p) g.peers.dst[p] = e->dist.peer_kv[buf][p];
+        if (overlap) ++e->dist.epoch;   // (the barrier form advances the epoch in engine_dist_barrier)
         g.peers.ld = 2 * D;
         g.peers.col0 = D;
         g.peers.row0 = e->tok0;
+        if (overlap) {
+            g.peers.n = 1;         // the projection writes this rank's slab of its OWN buffer only
+            g.peers.dst[0] = e->dist.kv[buf];
+            // ... which the copy engines may still be reading for the pushes of two blocks ago
+            if (e->dist.copied_valid[buf]) K5_CHECK_CUDA(cudaStreamWaitEvent(st, e->dist.ev_copied[buf], 0));
+        } else {
+            // all-gather fused into the projection: the K | V columns of this rank's rows go straight from the GEMM
+            // epilogue into every rank's [S, 2D] buffer over NVLink; one flag barrier, then attention over all of S
+            g.peers.n = e->dist.world;
+            for (int p = 0; p < e->dist.world; ++p) g.peers.dst[p] = e->dist.peer_kv[buf][p];
+        }
         kp = e->dist.kv[buf];
         vp = e->dist.kv[buf] + D;
         ldkv = 2 * D;
         Sk = e->S;
     }
     K5_TRY(lin_gemm(xn, D, b.self.qkv, M, EPI_HEADS, g, st));
-    if (shard) K5_TRY(engine_dist_barrier(e, st));
+    if (overlap) {
+        // Overlapped all-gather: copy engines push the slab to the peers (nearest consumer first: rank r-1 reads slab r
+        // right after its own) and flag each arrival, while the attention kernel below starts on the local slab and
+        // waits per slab inside its TMA producer.  A peer's buffer may only be overwritten once that peer has finished
+        // the attention that read it two blocks ago (FLAG_DONE), which the copy stream - not the compute stream - waits for.
+        Engine::Dist& d = e->dist;
+        const int W_ = d.world, r = d.rank;
+        K5_CHECK_CUDA(cudaEventRecord(d.ev_kv, st));
+        K5_CHECK_CUDA(cudaStreamWaitEvent(d.copy_st, d.ev_kv, 0));
+        // a wrap-safe ">= epoch - 2" on every peer's DONE slot (stream memory operations: no SM needed, so they make
+        // progress while the persistent attention kernel holds every SM - a signalling KERNEL on a second stream may not)
+        if (d.epoch > 2)
+            for (int p = 0; p < W_; ++p)
+                if (p != r) K5_TRY(stream_wait_geq_u32(d.copy_st, d.flags + FLAG_DONE + p, d.epoch - 2));
+        const size_t off = static_cast<size_t>(e->tok0) * 2 * D, bytes = static_cast<size_t>(e->Sl) * 2 * D * sizeof(bf16);
+        for (int k = 1; k < W_; ++k) {
+            const int p = (r - k + W_) % W_;
+            K5_CHECK_CUDA(cudaMemcpyAsync(d.peer_kv[buf][p] + off, d.kv[buf] + off, bytes, cudaMemcpyDeviceToDevice, d.copy_st));
+            K5_TRY(stream_write_u32(d.copy_st, d.peer_flags[p] + FLAG_READY + buf * 8 + r, d.epoch));
+        }
+        K5_CHECK_CUDA(cudaEventRecord(d.ev_copied[buf], d.copy_st));
+        d.copied_valid[buf] = true;
+        slabs.flags = d.flags + FLAG_READY + buf * 8;
+        slabs.epoch = d.epoch;
+        slabs.n = W_;
+        slabs.first = r;
+        const int base = e->T / W_, rem = e->T % W_;
+        for (int q = 0; q <= W_; ++q) slabs.row0[q] = (q * base + (q < rem ? q : rem)) * e->Hp * e->Wp;
+    } else if (shard) {
+        K5_TRY(engine_dist_barrier(e, st));
+    } else if (visual && e->dbg_world > 1 && !sp && (e->Hp * e->Wp) % 256 == 0) {
+        slabs.n = e->dbg_world;
+        slabs.first = -1;
+        const int base = e->T / slabs.n, rem = e->T % slabs.n;
+        for (int q = 0; q <= slabs.n; ++q) slabs.row0[q] = (q * base + (q < rem ? q : rem)) * e->Hp * e->Wp;
+    }
     const int32_t *cnt = nullptr, *idx = nullptr;
     if (sp) {
         count_launch(nabla_select_launches());
@@ -731,10 +813,15 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
     const bool timed = e->timing && visual && e->ev_used + 2 <= e->ev.size();
     if (timed) K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used], st));
     K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st, &e->sparse_ws,
-                         b.self.score_bound));
+                         b.self.score_bound, slabs.n > 0 ? &slabs : nullptr));
     if (timed) {
         K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used + 1], st));
         e->ev_used += 2;
+    }
+    if (overlap) {     // this rank no longer reads K|V buffer `buf` of this epoch: peers may push the block after next
+        for (int p = 0; p < e->dist.world; ++p)
+            if (p != e->dist.rank)
+                K5_TRY(stream_write_u32(st, e->dist.peer_flags[p] + FLAG_DONE + e->dist.rank, e->dist.epoch));
     }
     return out_proj_gate(e, att, b.self.o, x, mod + 2 * D, M, st);
 }

@@ -445,9 +445,12 @@ template <int BN, int EPI, int CL>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
     using Cfg = GemmCfg<BN, CL>;
     constexpr int NC = CL == 1 ? 1 : 2;
-    static int max_ctas = 0;           // CTAs that can be resident at once (whole clusters only when NC > 1)
+    static PerDevice<int> pd;          // CTAs that can be resident at once (whole clusters only when NC > 1), per device
     auto kern = gemm_bf16_kernel<BN, EPI, CL>;
-    if (max_ctas == 0) {
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lk(pd.m);
+    int& max_ctas = pd.v[dev];
+    if (!pd.set[dev]) {
         K5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         max_ctas = sm_count();
         if (NC > 1) {
@@ -468,6 +471,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, 
             K5_REQUIRE(n_clusters > 0, "GEMM: no thread-block cluster fits this device");
             max_ctas = n_clusters * NC;
         }
+        pd.set[dev] = true;
     }
     const int units = (((M + BM - 1) / BM + NC - 1) / NC) * (N / BN) * NC;
     const int grid = units < max_ctas ? units : max_ctas;

@@ -138,6 +138,21 @@ __device__ __forceinline__ void mbar_wait_lean_a(uint32_t bar, uint32_t parity) 
     }
 }
 
+// Polling with a pause between polls (nanosleep): for waits that have hundreds of cycles of slack.
+template <uint32_t SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_sleep_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+        "@P bra K5_DONE_%=;\n\t"
+        "K5_WAIT_%=:\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+        "@!P bra K5_WAIT_%=;\n\t"
+        "K5_DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity), "r"(SLEEP_NS)
+        : "memory");
+}
+
 // Wait used by the single-thread roles (TMA producer, MMA issuers), whose waits last a whole tile: the suspend-time
 // hint keeps the thread parked in hardware instead of re-issuing the poll every ~40 cycles, so the poll loop does
 // not take issue slots from the softmax warps that share its scheduler (measured: 33 polls x 6 instructions per tile

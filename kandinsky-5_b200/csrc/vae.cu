@@ -437,7 +437,9 @@ int decode_tile(Vae* e, const float* z, int Tz, int t0, int T, int H, int W, bf1
 int vae_decode(Vae* e, const float* z, int T, int H, int W, int tile_frames, int stride_frames, bf16* out, cudaStream_t st) {
     K5_REQUIRE(e->finalized, "vae_decode: call k5_vae_finalize first");
     K5_REQUIRE(z && out && T > 0 && H > 0 && W > 0, "vae_decode: bad arguments");
-    K5_REQUIRE(H <= e->c.max_height && W <= e->c.max_width && H * W <= e->c.max_height * e->c.max_width,
+    // every workspace size is symmetric in (H, W) - activations T*H*W*C, padded volume (T+2)(H+2)(W+2)*C, scores (T*H*W)^2 -
+    // so a portrait latent (96 x 64 for 768 x 512 pixels, t2v_pipeline.py:122-125) fits the landscape workspace
+    K5_REQUIRE((H <= e->c.max_height && W <= e->c.max_width) || (H <= e->c.max_width && W <= e->c.max_height),
                "vae_decode: latent larger than the engine's workspace");
     const int F = (T - 1) * 4 + 1, HH = 8 * H, WW = 8 * W;
     const int lat_min = tile_frames > 0 ? (tile_frames - 1) / 4 : 0;

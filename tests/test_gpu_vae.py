@@ -84,6 +84,25 @@ def test_decoder_matches_reference_golden(name):
     assert float((u8.float() - u8_ref.float()).abs().mean()) < 2.0
 
 
+def test_portrait_latent_decodes_in_the_landscape_workspace():
+    """768 x 512 pixels = latent 96 x 64 (t2v_pipeline.py:122-125) must decode in an engine sized for 64 x 96: here 12 x 8
+    in a workspace declared as 8 x 12, against the CPU oracle (bf16 rounding points on / off = the noise floor)."""
+    widths = (64, 64, 128, 128)
+    vae, sd = _build(widths, (5, 8, 12))
+    z = torch.randn(1, 16, 3, 12, 8, generator=torch.Generator().manual_seed(3))
+    out = vae.decode(z.cuda()).sample
+    assert out.shape == (1, 3, 9, 96, 64)
+    ref = VO.decode(sd, z, None)
+    VO.ROUNDING = False
+    try:
+        gold = VO.decode(sd, z, None)
+    finally:
+        VO.ROUNDING = True
+    own, oracle = rel_l2(out, gold), rel_l2(ref, gold)
+    print(f"portrait: engine-vs-fp32 {own:.2e}  oracle-vs-fp32 {oracle:.2e}  engine-vs-oracle {rel_l2(out, ref):.2e}")
+    assert own < 1.25 * oracle
+
+
 def test_decode_is_deterministic_and_tiles_agree_with_oracle_schedule():
     """Same latent twice -> identical video; the tiled schedule produces exactly 4 (T - 1) + 1 frames."""
     rec = torch.load(os.path.join(GOLD, "vae_tiled_9x8x8.pt"), weights_only=False)
