@@ -334,9 +334,8 @@ def synthetic_state_dict_gpu(cfg, device, seed=0):
     return sd
 
 
-def time_vae_decode(latent, dev):
-    """vae.decode of the latent the sampler produced, as generate_sample does it (generation_utils.py:210-222), through
-    the engine-backed AutoencoderKLHunyuanVideo mirror with random-init fp16 weights.  One warm-up, one timed decode."""
+def build_bench_vae(dev, H, W):
+    """Engine-backed AutoencoderKLHunyuanVideo mirror with random-init fp16 weights (the published VAE file is fp16)."""
     import torch
 
     from kandinsky.models.vae import AutoencoderKLHunyuanVideo, decoder_state_dict_shapes
@@ -354,11 +353,18 @@ def time_vae_decode(latent, dev):
                 fan_in *= d
             t = (torch.rand(shp, device=dev, generator=g) * 2 - 1) / fan_in ** 0.5
         sd[k] = t.half()
-    T, H, W, _ = latent.shape
     vae = AutoencoderKLHunyuanVideo(max_latent=(5, H, W))
     vae.load_state_dict(sd)
     vae.to(dev)
-    del sd
+    return vae
+
+
+def time_vae_decode(vae, latent, dev):
+    """vae.decode of the latent the sampler produced, as generate_sample does it (generation_utils.py:210-222), through
+    the engine-backed AutoencoderKLHunyuanVideo mirror.  One warm-up, one timed decode."""
+    import torch
+
+    T, H, W, _ = latent.shape
     z = (latent.reshape(1, T, H, W, -1) / vae.config.scaling_factor).permute(0, 4, 1, 2, 3).contiguous()
     z = z / z.std().clamp_min(1e-6)              # random-init DiT latents are not unit-scale; keep activations finite
     video = vae.decode(z).sample
@@ -377,6 +383,98 @@ def time_vae_decode(latent, dev):
     return {"ms": ms, "tiles": tiles, "frames": int(u8.shape[2]), "height": int(u8.shape[3]), "width": int(u8.shape[4]),
             "algorithmic_tflop": tflop, "tflops_achieved": tflop / ms * 1e3, "frac_of_sustained_peak": tflop / ms * 1e3 / sustained,
             "peak_source": src, "api": "kandinsky.models.vae.AutoencoderKLHunyuanVideo.decode -> k5_vae_decode (+ uint8 conversion)"}
+
+
+class CachedTextEmbedder:
+    """Stand-in for Kandinsky5TextEmbedder.encode (text_embedders.py) returning cached synthetic embeddings held in
+    PINNED HOST memory, as BASELINE.json's configs prescribe (Qwen2.5-VL / CLIP are outside the hot path)."""
+
+    def __init__(self, L, Ln):
+        import torch
+
+        g = torch.Generator().manual_seed(1)
+        self.pos = {"text_embeds": torch.randn(L, 3584, generator=g).to(torch.bfloat16).pin_memory(),
+                    "pooled_embed": torch.randn(1, 768, generator=g).to(torch.bfloat16).pin_memory()}
+        self.neg = {"text_embeds": torch.randn(Ln, 3584, generator=g).to(torch.bfloat16).pin_memory(),
+                    "pooled_embed": torch.randn(1, 768, generator=g).to(torch.bfloat16).pin_memory()}
+
+    def encode(self, texts, type_of_content="video"):
+        import torch
+
+        e = self.pos if texts[0] else self.neg
+        return dict(e), torch.tensor([0, e["text_embeds"].shape[0]], dtype=torch.int32)
+
+
+def other_configs(model, vae, dev, args):
+    """BASELINE.json configs 3, 4 and 5 as short samples on the same engine (N = 1 only; the headline line stays
+    config 2).  Config 5 is ONE call of the pipeline's generate_sample - 16 NFE + VAE decode + uint8, text embeddings
+    from pinned host memory, the video read back to the host - timed by the wall clock around the call."""
+    import torch
+
+    from kandinsky.generation_utils import generate, generate_sample
+
+    out = {}
+    sustained, _, _ = measured_peaks()
+
+    def conf_for(wl):
+        att = {"type": "nabla", **wl["nabla"]} if wl["nabla"] else {"type": "flash"}
+        return {"metrics": {"scale_factor": (1.0, 2.0, 2.0)}, "model": {"dit_params": dict(LITE), "attention": att}}
+
+    def sampler_steps(wl, steps, warm):
+        T, H, W, L, Ln = wl["T"], wl["H"], wl["W"], wl["L"], wl["Ln"]
+        S = T * (H // 2) * (W // 2)
+        emb = CachedTextEmbedder(L, Ln)
+        te = {k: v.to(dev) for k, v in emb.pos.items()}
+        nte = {k: v.to(dev) for k, v in emb.neg.items()}
+        noise = torch.randn(T, H, W, 16, device=dev, generator=torch.Generator(device=dev).manual_seed(6554))
+        pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+
+        def run(n):
+            return generate(model, dev, (T, H, W, 16), n, te, nte, pos, torch.arange(L), torch.arange(Ln), wl["w"],
+                            wl["sched"], conf_for(wl), noise=noise)
+
+        if warm:
+            run(warm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lat = run(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(lat).all()), "non-finite latent"
+        ms = e0.elapsed_time(e1) / steps
+        fwd = 2 if abs(wl["w"] - 1.0) > 1e-6 else 1
+        rho = model.last_sparse_density() if wl["nabla"] else 1.0
+        fl = dit_flops(S, L, rho) * fwd
+        return {"workload": wl["name"], "tokens": S, "forwards_per_step": fwd, "steps_timed": steps, "ms_per_step": ms,
+                "tokens_per_s": S * fwd / (ms * 1e-3), "nabla_density": rho if wl["nabla"] else None,
+                "full_config_seconds_at_this_rate": ms * 1e-3 * wl["nfe"] / fwd,
+                "model_frac_of_sustained_peak": fl / (ms * 1e-3) / 1e12 / sustained}
+
+    out["config_3_5s_sft"] = sampler_steps(WORKLOADS["5s_sft"], 2, 0)
+    if model.max_tokens >= 93696:
+        out["config_4_10s_sft_sta_only"] = sampler_steps(WORKLOADS["10s_sft_sta"], 2, 1)
+        out["config_4_10s_sft_nabla_P0.9"] = sampler_steps(WORKLOADS["10s_sft_nabla"], 1, 0)
+    if vae is not None:
+        # config 5: config_5s_distil = 16 NFE (w = 1) + VAE decode, one pipeline call
+        emb = CachedTextEmbedder(256, 64)
+        conf = conf_for(WORKLOADS["5s_nocfg"])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        video = generate_sample((1, 31, 64, 96, 16), "a synthetic prompt", model, vae, conf, text_embedder=emb, num_steps=16,
+                                guidance_weight=1.0, scheduler_scale=5.0, negative_caption="", seed=6554, device=dev,
+                                vae_device=dev, progress=False)
+        host = video.cpu()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        assert host.dtype == torch.uint8 and tuple(host.shape) == (1, 3, 121, 512, 768)
+        h2d = sum(v.numel() * 2 for v in emb.pos.values()) + sum(v.numel() * 2 for v in emb.neg.values())
+        out["config_5_5s_distil_e2e"] = {
+            "workload": "config_5s_distil: 768x512x121, 16 NFE (no CFG) + VAE decode (14 temporal tiles) -> uint8 video on the host",
+            "seconds": sec, "nfe": 16, "video_shape": list(host.shape), "h2d_bytes": h2d, "d2h_bytes": host.numel(),
+            "api": "kandinsky.generation_utils.generate_sample (k5_sample + k5_vae_decode), one call, wall clock",
+            "note": "random-init weights: the latent is not unit-scale, pixel values are not meaningful, the work is the same"}
+    return out
 
 
 def run_k5(args, wl):
@@ -402,7 +500,9 @@ def run_k5(args, wl):
     S = T * (H // 2) * (W // 2)
     cfg_on = abs(wl["w"] - 1.0) > 1e-6
     fwd_per_step = 2 if cfg_on else 1
-    model = DiffusionTransformer3D(**LITE, max_tokens=S, max_text_tokens=max(L, Ln))
+    with_configs = world == 1 and not args.no_configs and args.workload == "5s_nocfg"
+    # (the 10 s workloads of the `configs` block need the larger token workspace; buffer sizes do not change timings)
+    model = DiffusionTransformer3D(**LITE, max_tokens=max(S, 93696 if with_configs else 0), max_text_tokens=max(L, Ln))
     sd = synthetic_state_dict_gpu(LITE, dev, seed=0)
     model.load_state_dict(sd, assign=True)
     model.to(dev)
@@ -506,9 +606,12 @@ def run_k5(args, wl):
     d2h = h_out[f0:f0 + nf].numel() * 2
 
     # ---- VAE decode of the sampled latent (BASELINE.json configs[4], decode leg): reported beside the DiT metric ----
-    vae_info = None
+    vae_info, vae, configs = None, None, None
     if world == 1 and not args.no_vae and not wl["nabla"]:
-        vae_info = time_vae_decode(latent, dev)
+        vae = build_bench_vae(dev, H, W)
+        vae_info = time_vae_decode(vae, latent, dev)
+    if with_configs:
+        configs = other_configs(model, vae, dev, args)
 
     if rank != 0:
         if world > 1:
@@ -547,6 +650,8 @@ def run_k5(args, wl):
     }
     if vae_info is not None:
         line["vae_decode"] = vae_info
+    if configs is not None:
+        line["configs"] = configs
     if not args.no_cpu_baseline:
         v, m, cores, smp, kind = cpu_arm(wl, 20.0)
         line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": smp}
@@ -582,6 +687,8 @@ def main():
     ap.add_argument("--workload", default="5s_nocfg", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE-decode measurement that follows the DiT timing")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the short samples of BASELINE.json configs 3 / 4 / 5 that follow the headline measurement (N = 1)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -174,6 +174,7 @@ int k5_vae_decode(k5_vae* v, const float* z, int T, int H, int W, int tile_frame
 #define K5_EPI_GELU 1
 #define K5_EPI_GATE 2
 #define K5_EPI_HEADS 3
+#define K5_EPI_F32 4            /* out is float [M, N]: fp32 accumulators (+ bias), unrounded (scores for a softmax) */
 
 /* out[M,N] = epilogue(A[M,K] . W[N,K]^T); A, W, out, resid bf16; bias, gate, norm weights float32;
  * rope: float2 [M,32] (cos,sin).  See csrc/gemm.h for the epilogue semantics. */
@@ -213,7 +214,8 @@ int k5_sta_mask(int T, int Hb, int Wb, int wT, int wH, int wW, uint8_t* out, voi
 
 /* Causal 3x3x3 convolution on channels-last bf16 (HunyuanVideoCausalConv3d, vae.py:125-163).  x: [T, H, W, Cin];
  * w: the checkpoint layout [Cout, Cin, 3, 3, 3] in bf16; bias float32 [Cout]; resid (optional) / out: [T, H, W, Cout].
- * Cin, Cout multiples of 64.  workspace: bf16 [(T + 2) (H + 2) (W + 2) Cin + 27 Cout Cin].  (Parity-test entry
+ * Cin a multiple of 64; Cout a multiple of 64, or below 64 (conv_out's 3 channels; weight rows are zero-padded to 64).
+ * workspace: bf16 [(T + 2) (H + 2) (W + 2) Cin + 27 ceil64(Cout) Cin].  (Parity-test entry
  * point: pads, repacks and convolves; the engine keeps repacked weights and fuses GroupNorm + SiLU into the pad.) */
 int k5_conv3d_causal(const void* x, int T, int H, int W, int Cin, const void* w, int Cout, const float* bias,
                      const void* resid, void* out, void* workspace, void* stream);

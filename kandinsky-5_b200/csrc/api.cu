@@ -135,6 +135,7 @@ int k5_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, i
     K5_NEED(out);
     GemmEpilogue e;
     e.out = static_cast<bf16*>(out);
+    e.out_f32 = static_cast<float*>(out);        // K5_EPI_F32: `out` is an fp32 matrix
     e.ldo = ldo;
     e.bias = bias;
     e.resid = static_cast<const bf16*>(resid);
@@ -233,17 +234,19 @@ int k5_conv3d_causal(const void* x, int T, int H, int W, int Cin, const void* w,
     K5_NEED(bias);
     K5_NEED(out);
     K5_NEED(workspace);
-    if (Cin % 64 != 0 || Cout % 64 != 0) {
-        set_last_error("conv3d: Cin and Cout must be multiples of 64");
+    if (Cin % 64 != 0 || Cout <= 0 || (Cout % 64 != 0 && Cout > 64)) {
+        set_last_error("conv3d: Cin must be a multiple of 64, Cout a multiple of 64 or below 64 (conv_out)");
         return K5_ERR_INVALID;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Cout_pad = (Cout + 63) / 64 * 64;          // weight rows are padded with zeros (conv_out: 3 -> 64)
     bf16* pad = static_cast<bf16*>(workspace);
     bf16* wr = pad + static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * Cin;
     count_launch(3);
     K5_TRY(pad_gather(static_cast<const bf16*>(x), T, H, W, Cin, 1, 1, 1, nullptr, nullptr, nullptr, 32, false, pad, st));
+    if (Cout_pad != Cout) K5_CHECK_CUDA(cudaMemsetAsync(wr, 0, static_cast<size_t>(Cout_pad) * 27 * Cin * sizeof(bf16), st));
     K5_TRY(repack_conv_weight(w, 1, Cout, Cin, 27, Cin, wr, st));
-    return conv3d_causal(pad, T, H, W, Cin, wr, Cout, Cout, bias, static_cast<const bf16*>(resid), Cout,
+    return conv3d_causal(pad, T, H, W, Cin, wr, Cout, Cout_pad, bias, static_cast<const bf16*>(resid), Cout,
                          static_cast<bf16*>(out), Cout, st);
 }
 

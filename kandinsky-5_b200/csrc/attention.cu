@@ -133,6 +133,31 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
     p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
 }
 
+// Same without the clamp, for inputs known to lie in [-126, 126] (BOUNDED kernels: |x| <= score_bound <= 60).
+__device__ __forceinline__ void exp2_poly2_nc(float x0, float x1, float& p0, float& p1) {
+    const float MAGIC = 12582912.0f;
+    const uint64_t x = pack_f32x2(x0, x1);
+    const uint64_t xr = add_rm_f32x2(x, pack_f32x2(MAGIC, MAGIC));
+    const uint64_t xi = sub_f32x2(xr, pack_f32x2(MAGIC, MAGIC));
+    const uint64_t f = sub_f32x2(x, xi);
+    uint64_t p = fma_f32x2(f, pack_f32x2(0.077119089663028717f, 0.077119089663028717f),
+                           pack_f32x2(0.227564394474029541f, 0.227564394474029541f));
+    p = fma_f32x2(p, f, pack_f32x2(0.695146143436431885f, 0.695146143436431885f));
+    p = fma_f32x2(p, f, pack_f32x2(1.0f, 1.0f));
+    float r0, r1, q0, q1;
+    unpack_f32x2(xr, r0, r1);
+    unpack_f32x2(p, q0, q1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+// Dense BOUNDED kernel, tuning: pairs q with q % K5_ATTN_POLY_MOD == K5_ATTN_POLY_AT take the polynomial (0 = none)
+#ifndef K5_ATTN_POLY_MOD
+#define K5_ATTN_POLY_MOD 0
+#endif
+#ifndef K5_ATTN_POLY_AT
+#define K5_ATTN_POLY_AT 5
+#endif
+
 // NPOLY of every 8 element pairs take the polynomial path, the rest the MUFU.
 //
 // BOUNDED: the caller guarantees |q . k| * scale * log2(e) <= p.score_bound <= 60 for every query / key pair (the DiT
@@ -557,6 +582,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                          x0, x1);
                             if ((q & 7) < NPOLY) {
                                 exp2_poly2(x0, x1, p0, p1);
+                            } else if (K5_ATTN_POLY_MOD > 0 && !SPARSE && (q % (K5_ATTN_POLY_MOD > 0 ? K5_ATTN_POLY_MOD : 1)) == K5_ATTN_POLY_AT) {
+                                exp2_poly2_nc(x0, x1, p0, p1);
                             } else {
                                 p0 = fast_exp2(x0);
                                 p1 = fast_exp2(x1);

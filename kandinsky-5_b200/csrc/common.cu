@@ -1,5 +1,8 @@
 #include "common.h"
 
+#include <cstring>
+#include <unordered_map>
+
 #include <mutex>
 
 namespace k5 {
@@ -70,6 +73,30 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     K5_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
     K5_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
     K5_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+    // A forward encodes ~1000 maps and all of them recur every forward (same engine buffers, same shapes): the
+    // descriptor is a pure function of (device, base, shape, pitch, box), so it is cached instead of re-encoded.
+    struct Key {
+        uint64_t v[6];
+        bool operator==(const Key& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+    };
+    struct Hash {
+        size_t operator()(const Key& k) const {
+            uint64_t h = 0x9e3779b97f4a7c15ull;
+            for (uint64_t x : k.v) h = (h ^ x) * 0xff51afd7ed558ccdull + (h >> 29);
+            return static_cast<size_t>(h);
+        }
+    };
+    static std::mutex m;
+    static std::unordered_map<Key, CUtensorMap, Hash> cache;
+    const Key key = {{reinterpret_cast<uint64_t>(base), rows, cols, ld, box_rows, static_cast<uint64_t>(current_device())}};
+    {
+        std::lock_guard<std::mutex> lk(m);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return K5_OK;
+        }
+    }
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {64, box_rows};
@@ -81,6 +108,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
         set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
         return K5_ERR_CUDA;
     }
+    std::lock_guard<std::mutex> lk(m);
+    if (cache.size() >= 8192) cache.clear();        // callers with ever-changing pointers (tests) must not grow it
+    cache.emplace(key, *out);
     return K5_OK;
 }
 

@@ -100,6 +100,8 @@ struct Engine {
     Lin text_in, vis_in, out_lin, pooled_in;
     float *text_ln_w = nullptr, *text_ln_b = nullptr, *pooled_ln_w = nullptr, *pooled_ln_b = nullptr;
     std::vector<Block> tblocks, vblocks;
+    Lin ckv_all;                    // [num_visual_blocks * 2D, D]: every block's cross-attention [Wk | Wv], stacked
+    float* ckn_all = nullptr;       // [num_visual_blocks, 64] key-norm weights of the cross-attentions
     size_t out_mod_off = 0;
     float *freqs = nullptr, *args_text = nullptr, *args_ax[3] = {nullptr, nullptr, nullptr};
 
@@ -206,17 +208,23 @@ void expect_attn(Engine* e, const std::string& p) {
     e->expected.insert(p + "key_norm.weight");
 }
 
-int alloc_attn(Engine* e, AttnW& a, bool cross) {
+// cross_slot >= 0: cross-attention of visual block `cross_slot`; its K | V projection and key-norm weight are slices of
+// the engine-wide stacks (Engine::ckv_all), so that one GEMM projects the text for all blocks at once
+int alloc_attn(Engine* e, AttnW& a, int cross_slot = -1) {
     const int D = e->D;
-    if (!cross) {
+    if (cross_slot < 0) {
         K5_TRY(e->alloc_lin(a.qkv, 3 * D, D, true));
+        K5_TRY(e->alloc(&a.kn, 64));
     } else {
         K5_TRY(e->alloc_lin(a.qkv, D, D, true));
-        K5_TRY(e->alloc_lin(a.kv, 2 * D, D, true));
+        a.kv.out = 2 * D;
+        a.kv.in = a.kv.ld = D;
+        a.kv.W = e->ckv_all.W + static_cast<size_t>(cross_slot) * 2 * D * D;
+        a.kv.b = e->ckv_all.b + static_cast<size_t>(cross_slot) * 2 * D;
+        a.kn = e->ckn_all + static_cast<size_t>(cross_slot) * 64;
     }
     K5_TRY(e->alloc_lin(a.o, D, D, true));
     K5_TRY(e->alloc(&a.qn, 64));
-    K5_TRY(e->alloc(&a.kn, 64));
     return K5_OK;
 }
 
@@ -279,7 +287,7 @@ int engine_init(Engine* e) {
         Block& b = e->tblocks[i];
         b.mod_off = off;
         off += 6 * D;
-        K5_TRY(alloc_attn(e, b.self, false));
+        K5_TRY(alloc_attn(e, b.self));
         K5_TRY(e->alloc_lin(b.ff_in, F, D, false));
         K5_TRY(e->alloc_lin(b.ff_out, D, F, false));
         const std::string p = "text_transformer_blocks." + std::to_string(i) + ".";
@@ -289,12 +297,14 @@ int engine_init(Engine* e) {
         expect_lin(e, p + "feed_forward.out_layer", false);
     }
     e->vblocks.resize(c.num_visual_blocks);
+    K5_TRY(e->alloc_lin(e->ckv_all, c.num_visual_blocks * 2 * D, D, true));
+    K5_TRY(e->alloc(&e->ckn_all, static_cast<size_t>(c.num_visual_blocks) * 64));
     for (int i = 0; i < c.num_visual_blocks; ++i) {
         Block& b = e->vblocks[i];
         b.mod_off = off;
         off += 9 * D;
-        K5_TRY(alloc_attn(e, b.self, false));
-        K5_TRY(alloc_attn(e, b.cross, true));
+        K5_TRY(alloc_attn(e, b.self));
+        K5_TRY(alloc_attn(e, b.cross, i));
         K5_TRY(e->alloc_lin(b.ff_in, F, D, false));
         K5_TRY(e->alloc_lin(b.ff_out, D, F, false));
         const std::string p = "visual_transformer_blocks." + std::to_string(i) + ".";
@@ -320,7 +330,7 @@ int engine_init(Engine* e) {
     K5_TRY(e->alloc(&e->tatt, L * D));
     K5_TRY(e->alloc(&e->thid, L * F));
     K5_TRY(e->alloc(&e->tproj, L * D));
-    K5_TRY(e->alloc(&e->ckv, L * 2 * D));
+    K5_TRY(e->alloc(&e->ckv, L * 2 * D * c.num_visual_blocks));     // cross-attention K | V of ALL visual blocks
     K5_TRY(e->alloc(&e->tfeat, D));
     K5_TRY(e->alloc(&e->t1, Td));
     K5_TRY(e->alloc(&e->tembed, Td));
@@ -826,7 +836,24 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
     return out_proj_gate(e, att, b.self.o, x, mod + 2 * D, M, st);
 }
 
-int cross_attention(Engine* e, const Block& b, const bf16* text, int L, const float* mod, cudaStream_t st) {
+// Cross-attention K | V of every visual block in ONE GEMM (dit.py:170-171 hands the same text_embed to all blocks;
+// nn.py:317-319,343-349: k = RMSNorm(to_key(text)), v = to_value(text), no RoPE): [L, D] x [NB * 2D, D]^T with the head
+// epilogue in stacked-group mode (period 2D, first D columns of a group normed with that block's key_norm weight).
+// Replaces 32 launches of 28 tiles each (19 % of the SMs) by one launch of 2 x 448 tiles.
+int cross_kv_all(Engine* e, const bf16* text, int L, cudaStream_t st) {
+    const int D = e->D;
+    GemmEpilogue g;
+    g.out = e->ckv;
+    g.ldo = 2 * D * static_cast<int>(e->vblocks.size());
+    g.norm_w0 = e->ckn_all;
+    g.norm_w1 = e->ckn_all;
+    g.norm_split = D;
+    g.norm_cols = D;
+    g.norm_period = 2 * D;
+    return lin_gemm(text, D, e->ckv_all, L, EPI_HEADS, g, st);
+}
+
+int cross_attention(Engine* e, const Block& b, int L, const float* mod, cudaStream_t st) {
     const int D = e->D, M = e->Sl;
     count_launch(1);
     K5_TRY(ln_rows(e->x, D, e->xn, D, M, D, mod + D, mod, true, LN_EPS, st));
@@ -838,16 +865,11 @@ int cross_attention(Engine* e, const Block& b, const bf16* text, int L, const fl
     gq.norm_split = D;
     gq.norm_cols = D;
     K5_TRY(lin_gemm(e->xn, D, b.cross.qkv, M, EPI_HEADS, gq, st));
-    GemmEpilogue gk;                 // [k | v] = text . [Wk | Wv]^T, k normed
-    gk.out = e->ckv;
-    gk.ldo = 2 * D;
-    gk.norm_w0 = b.cross.kn;
-    gk.norm_w1 = b.cross.kn;
-    gk.norm_split = D;
-    gk.norm_cols = D;
-    K5_TRY(lin_gemm(text, D, b.cross.kv, L, EPI_HEADS, gk, st));
+    // [k | v] of this block = columns [slot * 2D, (slot + 1) * 2D) of the stacked projection (cross_kv_all)
+    const int ldc = 2 * D * static_cast<int>(e->vblocks.size());
+    const bf16* kv = e->ckv + (&b - e->vblocks.data()) * 2 * D;
     count_launch(1);
-    K5_TRY(attention_fwd(e->qkv, D, e->ckv, 2 * D, e->ckv + D, 2 * D, e->att, D, M, L, e->heads, 0.125f, nullptr, nullptr, st,
+    K5_TRY(attention_fwd(e->qkv, D, kv, ldc, kv + D, ldc, e->att, D, M, L, e->heads, 0.125f, nullptr, nullptr, st,
                          nullptr, b.cross.score_bound));
     return out_proj_gate(e, e->att, b.cross.o, e->x, mod + 2 * D, M, st);
 }
@@ -935,10 +957,11 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
         K5_TRY(bf16_addsub(e->x, e->mag_res[mag_slot], e->x, nx, false, st));
     } else {
         if (mag_slot >= 0) K5_CHECK_CUDA(cudaMemcpyAsync(e->mag_x0, e->x, nx * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+        if (!e->vblocks.empty()) K5_TRY(cross_kv_all(e, e->te, L, st));
         for (const Block& b : e->vblocks) {
             const float* mod = e->modOut + b.mod_off;
             K5_TRY(self_attention(e, b, e->x, e->xn, e->qkv, e->att, mod, S, rope_v, sp, true, st));
-            K5_TRY(cross_attention(e, b, e->te, L, mod + 3 * D, st));
+            K5_TRY(cross_attention(e, b, L, mod + 3 * D, st));
             K5_TRY(feed_forward(e, b, e->x, e->xn, e->hid, mod + 6 * D, S, st));
         }
         if (mag_slot >= 0) {

@@ -267,7 +267,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     // Rounding points of the reference (bf16 Linear output; bf16 after RMSNorm; bf16 after RoPE) are kept,
                     // but a value that is only rounded to be packed right away is rounded once, by the pack itself.
-                    const bool normed = col0 < e.norm_cols;
+                    // norm_period > 0: the N axis is a stack of groups of norm_period columns (the cross-attention K | V
+                    // projections of all visual blocks in one GEMM), each with its own 64-float norm weight
+                    const int pc0 = e.norm_period > 0 ? col0 % e.norm_period : col0;
+                    const int grp64 = e.norm_period > 0 ? (col0 / e.norm_period) * 64 : 0;
+                    const bool normed = pc0 < e.norm_cols;
                     if (normed) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -275,7 +279,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             ss = fmaf(x[2 * i], x[2 * i], ss);
                             ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
                         }
-                        const float4* w4 = reinterpret_cast<const float4*>((col0 < e.norm_split) ? e.norm_w0 : e.norm_w1);
+                        const float4* w4 = reinterpret_cast<const float4*>(((pc0 < e.norm_split) ? e.norm_w0 : e.norm_w1) + grp64);
                         const float inv = rsqrtf(ss * (1.0f / 64.0f) + 1.1920928955078125e-07f);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -285,7 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             x[4 * i + 2] = x[4 * i + 2] * inv * w.z;
                             x[4 * i + 3] = x[4 * i + 3] * inv * w.w;
                         }
-                        if (col0 < e.rope_cols && has_rope) {
+                        if (pc0 < e.rope_cols && has_rope) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 const float4 cs = rope_row[i];          // (cos, sin) of pairs 2i and 2i + 1
@@ -361,6 +365,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tmem_ld32(t_row + c * 64 + 32, raw + 32);
                     tmem_wait_ld();
                     const int col0 = n0 + c * 64;
+                    if constexpr (EPI == EPI_F32) {
+                        // unrounded scores for a softmax (VAE mid-block attention): thread = row, 256 contiguous bytes
+                        if (row_ok) {
+                            float4* dst = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + col0);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + i);
+                                dst[i] = make_float4(__uint_as_float(raw[4 * i]) + b.x, __uint_as_float(raw[4 * i + 1]) + b.y,
+                                                     __uint_as_float(raw[4 * i + 2]) + b.z, __uint_as_float(raw[4 * i + 3]) + b.w);
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float y[8];
@@ -423,6 +440,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         *reinterpret_cast<uint4*>(e.out + static_cast<size_t>(rr) * e.ldo + col0 + chunk * 8) = o;
                     }
+                    }   // EPI != EPI_F32
                 }
             }
             tc_fence_before();
@@ -504,6 +522,7 @@ int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
         case EPI_GELU: return launch<BN, EPI_GELU, CL>(tmA, tmB, M, N, K, e, st);
         case EPI_GATE: return launch<BN, EPI_GATE, CL>(tmA, tmB, M, N, K, e, st);
         case EPI_HEADS: return launch<BN, EPI_HEADS, CL>(tmA, tmB, M, N, K, e, st);
+        case EPI_F32: return launch<BN, EPI_F32, CL>(tmA, tmB, M, N, K, e, st);
     }
     set_last_error("unknown GEMM epilogue");
     return K5_ERR_INVALID;
@@ -516,7 +535,9 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
     K5_REQUIRE(M > 0 && N > 0 && K > 0, "GEMM: empty problem");
     K5_REQUIRE(N % 64 == 0, "GEMM: N must be a multiple of 64");
     K5_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "GEMM: K / pitches must be multiples of 8 elements");
-    K5_REQUIRE(e.out != nullptr && e.ldo % 8 == 0, "GEMM: output pitch must be a multiple of 8 elements");
+    K5_REQUIRE((epi == EPI_F32 ? static_cast<const void*>(e.out_f32) : static_cast<const void*>(e.out)) != nullptr && e.ldo % 8 == 0,
+               "GEMM: output pitch must be a multiple of 8 elements");
+    K5_REQUIRE(epi != EPI_F32 || (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0, "GEMM: fp32 output must be 16-byte aligned");
     if (epi == EPI_GATE) K5_REQUIRE(e.resid && e.gate && e.ldr % 8 == 0, "GEMM: gate epilogue needs resid/gate");
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     K5_REQUIRE(al16(e.bias) && al16(e.gate) && al16(e.norm_w0) && al16(e.norm_w1) && al16(e.rope),
@@ -525,6 +546,8 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
         K5_REQUIRE(e.norm_cols % 64 == 0 && e.norm_split % 64 == 0 && e.rope_cols % 64 == 0, "GEMM: head split must be x64");
         K5_REQUIRE(e.norm_cols == 0 || (e.norm_w0 && e.norm_w1), "GEMM: head epilogue needs norm weights");
         K5_REQUIRE(e.rope_cols == 0 || e.rope, "GEMM: head epilogue needs a rope table");
+        K5_REQUIRE(e.norm_period >= 0 && e.norm_period % 64 == 0 && (e.norm_period == 0 || e.peers.n == 0),
+                   "GEMM: the norm period must be x64 and excludes the peer scatter");
         K5_REQUIRE(e.peers.n >= 0 && e.peers.n <= MAX_PEERS, "GEMM: at most 8 scatter destinations");
         K5_REQUIRE(e.peers.n == 0 || (e.peers.col0 % 64 == 0 && e.peers.ld % 8 == 0), "GEMM: scatter split must be x64");
     } else {

@@ -3,7 +3,7 @@
 
 namespace k5 {
 
-enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GATE = 2, EPI_HEADS = 3 };
+enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GATE = 2, EPI_HEADS = 3, EPI_F32 = 4 };
 
 // Fused all-gather of the temporal shard (EPI_HEADS only): output columns >= col0 (the K | V part of the fused
 // QKV projection) are not written to `out` but to row (row0 + m), column (n - col0) of every destination in
@@ -21,6 +21,7 @@ struct PeerScatter {
 
 struct GemmEpilogue {
     bf16* out = nullptr;            // [M, N] row-major, pitch ldo
+    float* out_f32 = nullptr;       // EPI_F32: the fp32 accumulators (+ bias) are stored unrounded, pitch ldo (elements)
     int ldo = 0;
     const float* bias = nullptr;    // [N] (bf16-representable values held in fp32) or null
     // EPI_GATE: out = bf16(resid + gate * bf16(acc + bias)); out may alias resid
@@ -31,9 +32,12 @@ struct GemmEpilogue {
     // columns < norm_split and norm_w1 otherwise; columns [0, rope_cols) then get RoPE.
     const float* norm_w0 = nullptr;
     const float* norm_w1 = nullptr;
+    // norm_period > 0: N is a stack of groups of norm_period columns; the three column limits then apply to the
+    // column WITHIN its group, and group g uses norm_w0 + 64 g / norm_w1 + 64 g (weights stacked [groups, 64]).
     int norm_split = 0;
     int norm_cols = 0;
     int rope_cols = 0;
+    int norm_period = 0;
     const float2* rope = nullptr;   // [M, 32] (cos, sin) per row and rotation pair
     PeerScatter peers;              // n == 0: everything goes to `out`
 };

@@ -72,7 +72,8 @@ struct Vae {
     // workspace
     bf16* buf[3] = {nullptr, nullptr, nullptr};       // activations [P, C]
     bf16* pad = nullptr;                              // padded conv input
-    bf16 *scores = nullptr, *vt = nullptr;            // attention: S / P [N, N], V^T [C, N]
+    float* scores = nullptr;                          // attention: S [N, N] fp32
+    bf16 *probs = nullptr, *vt = nullptr;             // P [N, N] bf16, V^T [C, N]
     bf16* tile[2] = {nullptr, nullptr};               // decoded tiles [F, 8H, 8W, 3]
     double* sums = nullptr;
     float *stats = nullptr, *ones = nullptr;
@@ -210,10 +211,12 @@ int vae_init(Vae* e) {
         for (int i = 0; i < 3; ++i) K5_TRY(e->alloc(&e->buf[i], max_act));
         K5_TRY(e->alloc(&e->pad, max_pad));
         K5_TRY(e->alloc(&e->scores, N * N));
+        K5_TRY(e->alloc(&e->probs, N * N));
         K5_TRY(e->alloc(&e->vt, N * top));
         for (int i = 0; i < 2; ++i) K5_TRY(e->alloc(&e->tile[i], T * H * W * 3));
     }
-    K5_TRY(e->alloc(&e->sums, 2 * 2048));
+    K5_TRY(e->alloc(&e->sums, static_cast<size_t>(GN_MAX_BLOCKS) * 2 *
+                                  std::max(std::max(e->width[0], e->width[1]), std::max(e->width[2], e->width[3]))));   // block partials
     K5_TRY(e->alloc(&e->stats, 2 * GROUPS));
     K5_TRY(e->alloc(&e->ones, 2048));
     {
@@ -315,9 +318,9 @@ namespace {
 
 int group_stats(Vae* e, const bf16* x, size_t P, int C, cudaStream_t st) {
     count_launch(2);
-    K5_CHECK_CUDA(cudaMemsetAsync(e->sums, 0, 2 * C * sizeof(double), st));
-    K5_TRY(gn_channel_sums(x, P, C, e->sums, st));
-    return gn_finalize(e->sums, P, C, GROUPS, GN_EPS, e->stats, st);
+    int nblocks = 0;
+    K5_TRY(gn_channel_sums(x, P, C, e->sums, &nblocks, st));
+    return gn_finalize(e->sums, nblocks, P, C, GROUPS, GN_EPS, e->stats, st);
 }
 
 // GroupNorm + SiLU + pad, then the 3x3x3 convolution
@@ -379,15 +382,15 @@ int mid_attention(Vae* e, int xi, int T, int H, int W, cudaStream_t st) {
     for (int f = 0; f < T; ++f) {
         const int keys = (f + 1) * hw;                // frames <= f are visible
         GemmEpilogue gs;
-        gs.out = e->scores + static_cast<size_t>(f) * hw * N;
+        gs.out_f32 = e->scores + static_cast<size_t>(f) * hw * N;
         gs.ldo = N;
         count_launch(3);
-        K5_TRY(gemm_bf16(q + static_cast<size_t>(f) * hw * C, C, k, C, hw, keys, C, EPI_STORE, gs, st));
-        K5_TRY(softmax_frame_causal(e->scores, N, N, hw, scale, f * hw, hw, st));
+        K5_TRY(gemm_bf16(q + static_cast<size_t>(f) * hw * C, C, k, C, hw, keys, C, EPI_F32, gs, st));
+        K5_TRY(softmax_frame_causal(e->scores, N, N, e->probs, N, hw, scale, f * hw, hw, st));
         GemmEpilogue go;
         go.out = o + static_cast<size_t>(f) * hw * C;
         go.ldo = C;
-        K5_TRY(gemm_bf16(e->scores + static_cast<size_t>(f) * hw * N, N, e->vt, N, hw, C, keys, EPI_STORE, go, st));
+        K5_TRY(gemm_bf16(e->probs + static_cast<size_t>(f) * hw * N, N, e->vt, N, hw, C, keys, EPI_STORE, go, st));
     }
     GemmEpilogue g;                                    // x = bf16(bf16(to_out(o) + b) + x)
     g.out = x;

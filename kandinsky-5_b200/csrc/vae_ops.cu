@@ -29,7 +29,8 @@ __device__ __forceinline__ uint4 pack8(const float* y) {
 }
 
 // Thread = one 8-channel group (fixed for its lifetime) striding over positions; block partials are combined in
-// shared memory, one double atomicAdd per channel per block.
+// shared memory and written to the block's own row of `sums` ([gridDim.x][2 C] doubles): no atomics, so the
+// statistics - and with them the whole decode - are bit-reproducible from run to run.
 __global__ void __launch_bounds__(256) gn_sums_kernel(const bf16* __restrict__ x, size_t P, int C, double* __restrict__ sums) {
     extern __shared__ float sh[];                   // [256][16]
     const int cg = C / 8;                            // channel groups per position
@@ -64,21 +65,38 @@ __global__ void __launch_bounds__(256) gn_sums_kernel(const bf16* __restrict__ x
             a += sh[(l * cg + sl) * 16 + j];
             b += sh[(l * cg + sl) * 16 + 8 + j];
         }
-        atomicAdd(sums + c, a);
-        atomicAdd(sums + C + c, b);
+        sums[static_cast<size_t>(blockIdx.x) * 2 * C + c] = a;
+        sums[static_cast<size_t>(blockIdx.x) * 2 * C + C + c] = b;
     }
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, double count, int C, int groups, float eps,
-                                   float* __restrict__ mean_rstd) {
-    const int g = threadIdx.x;
-    if (g >= groups) return;
+// One block per group: the (block, channel) partials of the group are summed in a fixed order (strided per thread,
+// then a shared-memory tree), in double.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restrict__ sums, int nblocks, double count, int C,
+                                                          int groups, float eps, float* __restrict__ mean_rstd) {
+    __shared__ double ra[256], rb[256];
+    const int g = blockIdx.x;
     const int cpg = C / groups;
     double a = 0.0, b = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        a += sums[c];
-        b += sums[C + c];
+    for (int e = threadIdx.x; e < nblocks * cpg; e += 256) {
+        const size_t row = static_cast<size_t>(e / cpg) * 2 * C;
+        const int c = g * cpg + e % cpg;
+        a += sums[row + c];
+        b += sums[row + C + c];
     }
+    ra[threadIdx.x] = a;
+    rb[threadIdx.x] = b;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            ra[threadIdx.x] += ra[threadIdx.x + w];
+            rb[threadIdx.x] += rb[threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    a = ra[0];
+    b = rb[0];
     const double n = count * cpg;
     const double mean = a / n;
     double var = b / n - mean * mean;
@@ -205,19 +223,27 @@ post_quant_pad_kernel(const float* __restrict__ z, int Cz, int Tz, int H, int W,
     }
 }
 
-// one block per row; the row (up to 5 * 6144 columns) is streamed three times from L2 / HBM
+// one block per row; the fp32 score row (up to 5 * 6144 columns) is streamed three times from L2 / HBM and the
+// probabilities leave as bf16 (the only rounding: the reference's SDPA keeps scores and softmax in fp32 too)
 __global__ void __launch_bounds__(256)
-softmax_frame_causal_kernel(bf16* __restrict__ s, int lds, int hw, float scale_log2, int row0) {
+softmax_frame_causal_kernel(const float* __restrict__ s, int lds, bf16* __restrict__ p, int ldp, int hw, float scale_log2,
+                            int row0) {
     __shared__ float red[8];
     const int r = row0 + blockIdx.x;
     const int n = (r / hw + 1) * hw;                 // visible columns (multiple of hw; hw is a multiple of 8)
-    uint4* row = reinterpret_cast<uint4*>(s + static_cast<size_t>(r) * lds);
+    const float4* row = reinterpret_cast<const float4*>(s + static_cast<size_t>(r) * lds);
+    uint4* out = reinterpret_cast<uint4*>(p + static_cast<size_t>(r) * ldp);
     const int nv = n / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto load8 = [&](int i, float* v) {
+        const float4 a = row[2 * i], b = row[2 * i + 1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    };
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
         float v[8];
-        unpack8(row[i], v);
+        load8(i, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) mx = fmaxf(mx, v[j]);
     }
@@ -231,7 +257,7 @@ softmax_frame_causal_kernel(bf16* __restrict__ s, int lds, int hw, float scale_l
     float sum = 0.f;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
         float v[8];
-        unpack8(row[i], v);
+        load8(i, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) sum += exp2f((v[j] - mx) * scale_log2);
     }
@@ -244,10 +270,10 @@ softmax_frame_causal_kernel(bf16* __restrict__ s, int lds, int hw, float scale_l
     const float inv = 1.0f / sum;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
         float v[8];
-        unpack8(row[i], v);
+        load8(i, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = exp2f((v[j] - mx) * scale_log2) * inv;
-        row[i] = pack8(v);
+        out[i] = pack8(v);
     }
 }
 
@@ -314,20 +340,22 @@ int blocks_for(size_t work, int threads) {
 
 }  // namespace
 
-int gn_channel_sums(const bf16* x, size_t P, int C, double* sums, cudaStream_t st) {
+int gn_channel_sums(const bf16* x, size_t P, int C, double* sums, int* nblocks, cudaStream_t st) {
     K5_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "GroupNorm: channel count must be 8 * a divisor of 256");
+    K5_REQUIRE(nblocks != nullptr, "GroupNorm: null block count");
     const int pos_per_block = 256 / (C / 8);
     size_t want = (P + pos_per_block * 8 - 1) / (static_cast<size_t>(pos_per_block) * 8);
-    const size_t cap = static_cast<size_t>(sm_count()) * 8;
+    const size_t cap = GN_MAX_BLOCKS;
     const int grid = static_cast<int>(want < cap ? (want ? want : 1) : cap);
     gn_sums_kernel<<<grid, 256, 256 * 16 * sizeof(float), st>>>(x, P, C, sums);
     K5_CHECK_CUDA(cudaGetLastError());
+    *nblocks = grid;
     return K5_OK;
 }
 
-int gn_finalize(const double* sums, size_t P, int C, int groups, float eps, float* mean_rstd, cudaStream_t st) {
-    K5_REQUIRE(groups > 0 && groups <= 1024 && C % groups == 0, "GroupNorm: bad group count");
-    gn_finalize_kernel<<<1, ((groups + 31) / 32) * 32, 0, st>>>(sums, static_cast<double>(P), C, groups, eps, mean_rstd);
+int gn_finalize(const double* sums, int nblocks, size_t P, int C, int groups, float eps, float* mean_rstd, cudaStream_t st) {
+    K5_REQUIRE(groups > 0 && groups <= 1024 && C % groups == 0 && nblocks > 0, "GroupNorm: bad group count");
+    gn_finalize_kernel<<<groups, 256, 0, st>>>(sums, nblocks, static_cast<double>(P), C, groups, eps, mean_rstd);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }
@@ -362,10 +390,12 @@ int post_quant_pad(const float* z, int Cz, int T, int H, int W, int t0, int Tz, 
     return K5_OK;
 }
 
-int softmax_frame_causal(bf16* s, int N, int lds, int hw, float scale, int row0, int rows, cudaStream_t st) {
-    K5_REQUIRE(hw % 8 == 0 && lds % 8 == 0 && N % hw == 0 && row0 >= 0 && row0 + rows <= N, "softmax: bad arguments");
+int softmax_frame_causal(const float* s, int N, int lds, bf16* p, int ldp, int hw, float scale, int row0, int rows,
+                         cudaStream_t st) {
+    K5_REQUIRE(hw % 8 == 0 && lds % 8 == 0 && ldp % 8 == 0 && N % hw == 0 && row0 >= 0 && row0 + rows <= N && s && p,
+               "softmax: bad arguments");
     if (rows <= 0) return K5_OK;
-    softmax_frame_causal_kernel<<<rows, 256, 0, st>>>(s, lds, hw, scale * 1.4426950408889634f, row0);
+    softmax_frame_causal_kernel<<<rows, 256, 0, st>>>(s, lds, p, ldp, hw, scale * 1.4426950408889634f, row0);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }

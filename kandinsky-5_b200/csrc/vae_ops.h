@@ -5,11 +5,12 @@ namespace k5 {
 
 // HBM-bound passes of the VAE decoder (kandinsky/models/vae.py); channels-last bf16 activations [P, C].
 
-// Per-channel sum and sum of squares over P positions, accumulated in double: sums[0..C) and sums[C..2C).
-// `sums` must be zeroed by the caller (cudaMemsetAsync).
-int gn_channel_sums(const bf16* x, size_t P, int C, double* sums, cudaStream_t st);
-// GroupNorm(32 groups, eps) statistics from the channel sums: mean_rstd[2g] = mean, [2g + 1] = rstd.
-int gn_finalize(const double* sums, size_t P, int C, int groups, float eps, float* mean_rstd, cudaStream_t st);
+// Per-channel sum and sum of squares over P positions, in double, as one row of partials per thread block:
+// sums[b][0..C) and sums[b][C..2C) for b < *nblocks <= GN_MAX_BLOCKS (no atomics: bit-reproducible).
+constexpr int GN_MAX_BLOCKS = 1184;          // 8 blocks on each of 148 SMs
+int gn_channel_sums(const bf16* x, size_t P, int C, double* sums, int* nblocks, cudaStream_t st);
+// GroupNorm(32 groups, eps) statistics from the block partials (fixed summation order): mean_rstd[2g] = mean, [2g + 1] = rstd.
+int gn_finalize(const double* sums, int nblocks, size_t P, int C, int groups, float eps, float* mean_rstd, cudaStream_t st);
 
 // The gather that feeds every 3x3x3 convolution: builds the replicate-padded (2 frames in front, 1 pixel around),
 // optionally nearest-up-sampled, optionally GroupNorm + SiLU'd copy of x.
@@ -28,9 +29,10 @@ int gn_apply(const bf16* x, size_t P, int C, const float* mean_rstd, const float
 int post_quant_pad(const float* z, int Cz, int T, int H, int W, int t0, int Tz, const float* w, const float* b, bf16* out,
                    cudaStream_t st);
 
-// In-place masked softmax of the mid-block attention scores (vae.py:110-122, 343-359): row r of frame f = r / hw
-// keeps columns [0, (f + 1) * hw); s <- bf16(softmax(s * scale)) over them.
-int softmax_frame_causal(bf16* s, int N, int lds, int hw, float scale, int row0, int rows, cudaStream_t st);
+// Masked softmax of the mid-block attention scores (vae.py:110-122, 343-359): row r of frame f = r / hw keeps columns
+// [0, (f + 1) * hw); p <- bf16(softmax(s * scale)) over them, s fp32 (unrounded GEMM accumulators), all math fp32.
+int softmax_frame_causal(const float* s, int N, int lds, bf16* p, int ldp, int hw, float scale, int row0, int rows,
+                         cudaStream_t st);
 
 // Temporal tile assembly (vae.py:1144-1204, 928-936).  cur / prev: decoded tiles, channels-last [F, H, W, 3] bf16.
 // Writes `count` frames starting at local frame `src0` of cur into frames [dst0, dst0 + count) of the NCTHW bf16 output

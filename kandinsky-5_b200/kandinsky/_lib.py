@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("K5_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libk5.so")
 
 K5_OK, K5_ERR_INVALID, K5_ERR_CUDA, K5_ERR_STATE, K5_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-EPI_STORE, EPI_GELU, EPI_GATE, EPI_HEADS = 0, 1, 2, 3
+EPI_STORE, EPI_GELU, EPI_GATE, EPI_HEADS, EPI_F32 = 0, 1, 2, 3, 4
 DIST_HANDLE_BYTES = 192
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 

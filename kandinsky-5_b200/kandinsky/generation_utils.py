@@ -17,9 +17,27 @@ def _get(conf, path):
     return cur
 
 
+def sta_block_mask(T, H, W, wT=3, wH=3, wW=3, device="cuda"):
+    """Same matrix as the reference's fast_sta_nabla (models/utils.py:108-133): block (t, h, w) sees block (t', h', w')
+    iff |t - t'| <= wT // 2, |h - h'| <= wH // 2 and |w - w'| <= wW // 2; bool [T H W, T H W].  On a CUDA device it is
+    built by k5_sta_mask, elsewhere by index arithmetic."""
+    device = torch.device(device)
+    if device.type == "cuda":
+        from . import ops
+
+        with torch.cuda.device(device):
+            return ops.sta_mask(T, H, W, wT, wH, wW, device=device).bool()
+    i = torch.arange(T * H * W, device=device)
+    coords = (i // (H * W), (i // W) % H, i % W)
+    m = torch.ones(T * H * W, T * H * W, dtype=torch.bool, device=device)
+    for c, win in zip(coords, (wT, wH, wW)):
+        m &= (c[:, None] - c[None, :]).abs() <= win // 2
+    return m
+
+
 def get_sparse_params(conf, batch_embeds, device):
-    """generation_utils.py:10-36.  The STA mask itself is built on the device by the engine (k5_sta_mask) from
-    (wT, wH, wW); the dict keeps the reference's keys so that callers reading them keep working."""
+    """generation_utils.py:10-36, same keys and values ("sta_mask" is the [1, 1, n, n] bool block mask).  The engine
+    rebuilds the mask on the device from (wT, wH, wW) and reads only P / to_fractal / the windows."""
     patch = _get(conf, "model.dit_params.patch_size")
     assert patch[0] == 1
     T, H, W, _ = batch_embeds["visual"].shape
@@ -35,7 +53,7 @@ def get_sparse_params(conf, batch_embeds, device):
         return getattr(att, name, default)
 
     return {
-        "sta_mask": None,
+        "sta_mask": sta_block_mask(T, H // 8, W // 8, a("wT"), a("wH"), a("wW"), device=device)[None, None],
         "attention_type": att_type,
         "to_fractal": True,
         "P": a("P"),

@@ -208,6 +208,9 @@ class DiffusionTransformer3D(nn.Module):
     # ---- forward ---------------------------------------------------------------------------------------
     def set_grid(self, shape, visual_rope_pos, scale_factor, fractal):
         T, H, W = shape
+        if len(visual_rope_pos) != 3 or [len(p) for p in visual_rope_pos] != [T, H // 2, W // 2]:
+            raise ValueError(f"visual_rope_pos must hold {T}, {H // 2}, {W // 2} positions (dit.py:161), got "
+                             f"{[len(p) for p in visual_rope_pos]}")
         key = (T, H, W, tuple(float(s) for s in scale_factor), bool(fractal),
                tuple(tuple(int(v) for v in p.tolist()) for p in visual_rope_pos))
         if key == self._grid_key:
@@ -224,7 +227,9 @@ class DiffusionTransformer3D(nn.Module):
         sp = K5Sparse()
         sp.P = float(sparse_params["P"])
         sp.wT, sp.wH, sp.wW = int(sparse_params["wT"]), int(sparse_params["wH"]), int(sparse_params["wW"])
-        sp.add_sta = 1 if sparse_params.get("add_sta", True) else 0
+        # nablaT_v2 (models/utils.py:152) ORs the STA mask unconditionally - the reference never reads `add_sta` - so the
+        # engine does the same; the key is accepted for compatibility
+        sp.add_sta = 1
         return sp
 
     @torch.no_grad()
@@ -245,7 +250,10 @@ class DiffusionTransformer3D(nn.Module):
             L = text.shape[0]
             tpos = [int(v) for v in text_rope_pos.tolist()]
             tpos_arr = None if tpos == list(range(L)) else (c_int32 * L)(*tpos)
-            out = torch.empty(T, H, W, self.cfg["out_visual_dim"], device=self._device, dtype=torch.bfloat16)
+            # on a temporal shard the engine writes this rank's frames only (the slabs are gathered once, after the last
+            # step: parallelize.gather_frames); the other frames read as zeros, never as uninitialised memory
+            alloc = torch.zeros if self.dist_world > 1 else torch.empty
+            out = alloc(T, H, W, self.cfg["out_visual_dim"], device=self._device, dtype=torch.bfloat16)
             sp = self._sparse_struct(sparse_params)
             t = float(time.reshape(-1)[0].item()) if torch.is_tensor(time) else float(time)
             spp = ctypes.byref(sp) if sp is not None else None

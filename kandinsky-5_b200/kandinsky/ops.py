@@ -27,8 +27,9 @@ def linear(a, w, bias=None, epilogue="store", resid=None, gate=None, norm_w0=Non
     N = w.shape[0]
     assert w.shape[1] == K
     if out is None:
-        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
-    epi = {"store": _lib.EPI_STORE, "gelu": _lib.EPI_GELU, "gate": _lib.EPI_GATE, "heads": _lib.EPI_HEADS}[epilogue]
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if epilogue == "f32" else torch.bfloat16)
+    epi = {"store": _lib.EPI_STORE, "gelu": _lib.EPI_GELU, "gate": _lib.EPI_GATE, "heads": _lib.EPI_HEADS,
+           "f32": _lib.EPI_F32}[epilogue]
     check(lib().k5_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epi, ptr(out), out.stride(0),
                              ptr(_f32(bias)), ptr(resid), 0 if resid is None else resid.stride(0), ptr(_f32(gate)),
                              ptr(_f32(norm_w0)), ptr(_f32(norm_w1)), norm_split, norm_cols, rope_cols, ptr(_f32(rope)),

@@ -4,6 +4,40 @@ import torch
 from .generation_utils import generate_sample
 
 
+def to_pil_images(images):
+    """t2v_pipeline.py:166-169: uint8 [B, 3, 1, H, W] -> list of PIL RGB images (torchvision's ToPILImage on a CHW
+    uint8 tensor = the HWC byte array handed to PIL unchanged)."""
+    from PIL import Image
+
+    return [Image.fromarray(img.permute(1, 2, 0).contiguous().numpy(), mode="RGB") for img in images.squeeze(2).cpu()]
+
+
+def write_video(path, frames, fps=24, crf=5):
+    """t2v_pipeline.py:181-186: torchvision.io.write_video(path, [T, H, W, 3] frames, fps=24, options={"crf": "5"}).
+    torchvision's writer needs PyAV; where PyAV is not installed the same frames go through OpenCV's mp4 writer
+    (codec mp4v, no CRF control).  Returns the backend used."""
+    frames = torch.as_tensor(frames).to(torch.uint8).cpu()
+    assert frames.dim() == 4 and frames.shape[-1] == 3, "frames must be [T, H, W, 3]"
+    try:
+        import av  # noqa: F401
+        import torchvision
+
+        torchvision.io.write_video(path, frames.numpy(), fps=fps, options={"crf": str(crf)})
+        return "pyav"
+    except ImportError:
+        pass
+    import cv2
+
+    T, H, W, _ = frames.shape
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (W, H))
+    if not wr.isOpened():
+        raise RuntimeError(f"cannot open a video writer for {path}")
+    for f in frames.numpy():
+        wr.write(f[:, :, ::-1].copy())              # OpenCV takes BGR
+    wr.release()
+    return "opencv"
+
+
 class Kandinsky5T2VPipeline:
     def __init__(self, device_map, dit, text_embedder, vae, resolution=512, local_dit_rank=0, world_size=1, conf=None,
                  offload=False):
@@ -24,8 +58,9 @@ class Kandinsky5T2VPipeline:
                  scheduler_scale=10.0, negative_caption="Static, 2D cartoon, cartoon, 2d animation, paintings, images, "
                  "worst quality, low quality, ugly, deformed, walking backwards", expand_prompts=True, save_path=None,
                  progress=True):
-        """t2v_pipeline.py:90-189.  Prompt expansion (an LLM generate call) and mp4 writing are outside the hot path;
-        `expand_prompts` is accepted and ignored, `save_path` is honoured only for tensors (torch.save)."""
+        """t2v_pipeline.py:90-189: uint8 video [1, 3, F, H, W], or a list of PIL images when time_length == 0; `save_path`
+        (a path or a list with one path per result) writes png / mp4 on rank 0 exactly where the reference does.
+        Prompt expansion (an LLM generate call, :127-147) is outside the hot path: `expand_prompts` is accepted and ignored."""
         num_steps = self.num_steps if num_steps is None else num_steps
         guidance_weight = self.guidance_weight if guidance_weight is None else guidance_weight
         if seed is None:
@@ -46,6 +81,19 @@ class Kandinsky5T2VPipeline:
                               num_steps=num_steps, guidance_weight=guidance_weight, scheduler_scale=scheduler_scale,
                               negative_caption=negative_caption, seed=seed, device=self.device_map["dit"],
                               vae_device=self.device_map["vae"], progress=progress, offload=self.offload)
-        if save_path is not None and self.local_dit_rank == 0:
-            torch.save(out.cpu(), save_path)
+        if self.vae is None or self.local_dit_rank != 0:
+            return out                              # no decoder: the fp32 latent (generate_sample); ranks > 0: t2v_pipeline.py:165
+        if time_length == 0:
+            images = to_pil_images(out)
+            if save_path is not None:
+                paths = [save_path] if isinstance(save_path, str) else save_path
+                if len(paths) == len(images):
+                    for path, image in zip(paths, images):
+                        image.save(path)
+            return images
+        if save_path is not None:
+            paths = [save_path] if isinstance(save_path, str) else save_path
+            if len(paths) == len(out):
+                for path, video in zip(paths, out):
+                    write_video(path, video.permute(1, 2, 3, 0), fps=24, crf=5)
         return out

@@ -117,9 +117,9 @@ def resnet_block(sd, p, x):
     return _bf(h.float() + res.float())
 
 
-def frame_causal_mask(f, s):
+def frame_causal_mask(f, s, device=None):
     """prepare_causal_attention_mask (vae.py:110-122): token of frame i sees the tokens of frames <= i."""
-    m = torch.ones(f, f).tril_().log_()
+    m = torch.ones(f, f, device=device).tril_().log_()
     return m.repeat_interleave(s, 0).repeat_interleave(s, 1)
 
 
@@ -134,7 +134,7 @@ def mid_attention(sd, p, x):
         return _bf(_bf(t).float() @ _bf(sd[p + name + ".weight"]).float().t() + _bf(sd[p + name + ".bias"]).float())
 
     q, k, v = lin(n, "to_q"), lin(n, "to_k"), lin(n, "to_v")
-    sc = (q.float() @ k.float().transpose(-1, -2)) * (C ** -0.5) + frame_causal_mask(T, H * W)
+    sc = (q.float() @ k.float().transpose(-1, -2)) * (C ** -0.5) + frame_causal_mask(T, H * W, x.device)
     pr = torch.softmax(sc, dim=-1)
     o = _bf(_bf(pr).float() @ v.float())
     o = lin(o, "to_out.0")

@@ -49,6 +49,20 @@ def test_gemm_store_bias(M, N, K):
     assert rel_l2(out2, (a.float() @ w.float().t()).to(torch.bfloat16)) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 192, 512), (1536, 6144, 512), (257, 64, 1792)])
+def test_gemm_f32_scores_are_unrounded(M, N, K):
+    """K5_EPI_F32: the fp32 accumulators leave unrounded (scores of the VAE mid-block softmax, vae.py:343-359 + SDPA)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    a, w = _rand((M, K), 11), _rand((N, K), 12, K ** -0.5)
+    out = _ops().linear(a, w, None, epilogue="f32")
+    ref = a.float() @ w.float().t()
+    assert out.dtype == torch.float32 and out.shape == (M, N)
+    assert float((out - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))    # far below a bf16 ulp (4e-3)
+    bias = _rand((N,), 13).float()
+    out = _ops().linear(a, w, bias, epilogue="f32")
+    assert float((out - (ref + bias)).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()) + 4.0)
+
+
 def test_gemm_gelu():
     M, N, K = 640, 1024, 256
     a, w = _rand((M, K), 4), _rand((N, K), 5, K ** -0.5)
