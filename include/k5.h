@@ -114,6 +114,15 @@ int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, fl
               int L, const void* pooled, const void* null_text, int Ln, const void* null_pooled, const k5_sparse* sparse,
               void* stream);
 
+/* k5_sample with MagCache (kandinsky/magcache_utils.py:41-101 inside the loop of generation_utils.py:105-128).
+ * skip_schedule: host array of num_steps * 2 bytes; entry [2 i + slot] != 0 makes forward `slot` (0 = conditional,
+ * 1 = unconditional) of step i reuse the cached residual of its slot instead of running the visual blocks.  The
+ * decisions follow from the calibrated magnitude ratios alone (magcache_utils.py:64-80), so the caller computes them up
+ * front (the Python mirror's MagCacheState) and no host round trip is left inside the loop. */
+int k5_sample_magcache(k5_engine* e, float* img, int num_steps, float guidance_weight, float scheduler_scale,
+                       const void* text, int L, const void* pooled, const void* null_text, int Ln, const void* null_pooled,
+                       const k5_sparse* sparse, const uint8_t* skip_schedule, void* stream);
+
 /* ---- temporal shard over the GPUs of one node -------------------------------------------
  * The reference scales with a DTensor tensor-parallel plan (kandinsky/models/parallelize.py:11-102, entered from
  * kandinsky/utils.py:40-87 when WORLD_SIZE > 1); these entry points replace it: one engine per rank, rank r owns a

@@ -25,7 +25,8 @@ int engine_set_grid(Engine* e, int T, int H, int W, const int32_t* pt, const int
 int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, const int32_t* text_pos, const bf16* pooled,
                    float time, const k5_sparse* sp, bf16* out, cudaStream_t st, int mag_slot, int mag_skip);
 int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, const bf16* text, int L, const bf16* pooled,
-                  const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st);
+                  const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st,
+                  const uint8_t* skip_schedule = nullptr);
 float engine_density(Engine* e);
 int engine_timing(Engine* e, int enable, double* total_ms, int64_t* launches);
 int engine_dist_export(Engine* e, void* out);
@@ -102,6 +103,16 @@ int k5_sample(k5_engine* e, float* img, int num_steps, float guidance_weight, fl
                          static_cast<const bf16*>(text), L, static_cast<const bf16*>(pooled),
                          static_cast<const bf16*>(null_text), Ln, static_cast<const bf16*>(null_pooled), sparse,
                          static_cast<cudaStream_t>(stream));
+}
+int k5_sample_magcache(k5_engine* e, float* img, int num_steps, float guidance_weight, float scheduler_scale, const void* text,
+                       int L, const void* pooled, const void* null_text, int Ln, const void* null_pooled, const k5_sparse* sparse,
+                       const uint8_t* skip_schedule, void* stream) {
+    K5_NEED(e);
+    K5_NEED(skip_schedule);
+    return engine_sample(reinterpret_cast<Engine*>(e), img, num_steps, guidance_weight, scheduler_scale,
+                         static_cast<const bf16*>(text), L, static_cast<const bf16*>(pooled),
+                         static_cast<const bf16*>(null_text), Ln, static_cast<const bf16*>(null_pooled), sparse,
+                         static_cast<cudaStream_t>(stream), skip_schedule);
 }
 int k5_engine_attention_timing(k5_engine* e, int enable, double* total_ms, int64_t* launches) {
     K5_NEED(e);

@@ -133,7 +133,8 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
     p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
 }
 
-// Same without the clamp, for inputs known to lie in [-126, 126] (BOUNDED kernels: |x| <= score_bound <= 60).
+// Same without the clamp, for inputs known to lie in [-126, 126]: the dense BOUNDED kernel (|x| <= score_bound <= 60;
+// the columns of a ragged KV tail are masked with the finite score -126 / scale_log2 there, not with -inf).
 __device__ __forceinline__ void exp2_poly2_nc(float x0, float x1, float& p0, float& p1) {
     const float MAGIC = 12582912.0f;
     const uint64_t x = pack_f32x2(x0, x1);
@@ -151,11 +152,14 @@ __device__ __forceinline__ void exp2_poly2_nc(float x0, float x1, float& p0, flo
     p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
 }
 // Dense BOUNDED kernel, tuning: pairs q with q % K5_ATTN_POLY_MOD == K5_ATTN_POLY_AT take the polynomial (0 = none)
+// Measured (isolated, S = 47 616, two boxes, gpurun_out/r2_poly_nc.log): none 18.31 / 18.35 ms, every 8th 17.96 / 18.06,
+// every 6th 17.94 / 17.96, every 5th 18.01 / 18.02, every 4th 17.84 / 17.78 (pair 1 of 4) and 17.90 / 17.81 (pair 3 of 4);
+// with the clamp of the general path every 4th gave 17.96 / 18.11 and every 3rd 18.53 / 18.61 (slower than none).
 #ifndef K5_ATTN_POLY_MOD
-#define K5_ATTN_POLY_MOD 0
+#define K5_ATTN_POLY_MOD 4
 #endif
 #ifndef K5_ATTN_POLY_AT
-#define K5_ATTN_POLY_AT 5
+#define K5_ATTN_POLY_AT 1
 #endif
 
 // NPOLY of every 8 element pairs take the polynomial path, the rest the MUFU.
@@ -286,12 +290,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                     slab_tile = p.slab_tile0[slab];
                                     slab_left = p.slab_tile0[slab + 1] - slab_tile;
                                     if (p.slab_flags && slab != slab_own) {
-                                        const long long t0 = clock64();
-                                        for (;;) {
+                                        unsigned long long t0;
+                                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                                        for (uint32_t spins = 0;; ++spins) {
                                             uint32_t v;
                                             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.slab_flags + slab) : "memory");
                                             if (static_cast<int32_t>(v - p.slab_epoch) >= 0) break;
-                                            if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a peer died
+                                            if ((spins & 1023u) == 1023u) {       // a peer died or fell far behind: report, do not trap
+                                                unsigned long long t1;
+                                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                                                if (*p.slab_err != 0u) break;
+                                                if (t1 - t0 > p.slab_timeout_ns) {
+                                                    *p.slab_err = K5_DIST_ERR_SLAB;
+                                                    __threadfence_system();
+                                                    break;
+                                                }
+                                            }
                                         }
                                         asm volatile("fence.proxy.async;" ::: "memory");     // the TMA reads what a peer's copy wrote
                                     }
@@ -568,9 +582,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                 for (int c = (c0 > 64 ? c0 : 64); c < c1; ++c) s[c] = 0xff800000u;
                             }
                         } else if (tail) {
+                            // a finite "minus infinity": exp2 gives 2^-126 (P rounds to ~1e-38, times the zero-filled V rows
+                            // = 0; the row sum, >= 2^-60, does not see it), and the polynomial path needs no clamp
+                            const uint32_t masked = __float_as_uint(-126.0f / sl2);
 #pragma unroll
                             for (int c = c0; c < c1; ++c)
-                                if (c >= kv_rem) s[c] = 0xff800000u;      // -inf
+                                if (c >= kv_rem) s[c] = masked;
                         }
                     };
                     uint32_t dep = 0, p48 = 0;
@@ -1191,6 +1208,8 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.stagger = stagger;
     p.split_tail = split_tail;
     p.slab_flags = nullptr;
+    p.slab_err = nullptr;
+    p.slab_timeout_ns = 0;
     p.slab_epoch = 0;
     p.n_slabs = 0;
     p.slab_first = 0;
@@ -1208,7 +1227,10 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
                        "attention: the per-row debug order needs slab boundaries at multiples of 256 rows");
             p.slab_tile0[i] = slabs->row0[i] / KT;
         }
+        K5_REQUIRE(slabs->flags == nullptr || slabs->err != nullptr, "attention: slab flags need an error word");
         p.slab_flags = slabs->flags;
+        p.slab_err = slabs->err;
+        p.slab_timeout_ns = slabs->timeout_ns;
         p.slab_epoch = slabs->epoch;
         p.n_slabs = slabs->n;
         p.slab_first = slabs->first;

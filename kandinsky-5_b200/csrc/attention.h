@@ -20,6 +20,8 @@ struct AttnParams {
     // while the kernel runs.  The TMA producer walks the slabs starting at the rank's own one and, before the first
     // tile of a foreign slab, waits until slab_flags[slab] >= slab_epoch (written by the source rank after its copy).
     const uint32_t* slab_flags;   // null = everything is in place (no waiting)
+    volatile uint32_t* slab_err;  // mapped host word: set to K5_DIST_ERR_SLAB when a slab does not arrive in time
+    unsigned long long slab_timeout_ns;
 
     uint32_t slab_epoch;
     int n_slabs, slab_first;      // n_slabs == 0: natural tile order
@@ -40,8 +42,11 @@ struct AttnSparseWs {
 
 // O[Sq, heads*64] = softmax(Q K^T * softmax_scale) V per head, head_dim 64, non-causal.
 // Arrival schedule of the K | V rows for the overlapped all-gather of the temporal shard (see AttnParams).
+constexpr uint32_t K5_DIST_ERR_BARRIER = 1, K5_DIST_ERR_SLAB = 2;
 struct AttnSlabs {
     const uint32_t* flags = nullptr;
+    uint32_t* err = nullptr;      // see AttnParams::slab_err (required with flags)
+    unsigned long long timeout_ns = 600ull * 1000000000ull;
     uint32_t epoch = 0;
     int n = 0, first = 0;         // first = -1 (debug, flags == nullptr): every query row starts at the slab holding it
     int row0[9] = {};             // first row of each slab (multiples of 128); row0[n] = Sk

@@ -35,21 +35,38 @@ constexpr float LN_EPS = 1e-5f;
 // ---- temporal shard: cross-GPU barrier on flags in peer memory --------------------------------------------
 // Thread p publishes this rank's epoch into slot `rank` of rank p's flag array (release, system scope: the K/V
 // rows the preceding GEMM epilogue stored into p's buffer are visible before the flag), then waits until rank
-// p's epoch has arrived in the local array.  A wait that outlives ~20 s traps instead of hanging the GPU.
+// p's epoch has arrived in the local array.  A wait that outlives the time-out (K5_DIST_TIMEOUT_S, default 600 s: ranks
+// may be skewed by first-call allocations, rank-0-only I/O, text encoders) does not trap - a trap poisons the CUDA
+// context of every rank for good - but records a code in `err` (a word of mapped HOST memory the host reads before
+// every forward, engine_forward) and gives up; once the word is set every later wait returns at once, so the queue
+// drains and the next call reports the failure.
 struct PeerFlags {
     uint32_t* f[MAX_PEERS];
 };
-__global__ void dist_barrier_kernel(PeerFlags peers, uint32_t* mine, int rank, int world, uint32_t epoch) {
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void dist_barrier_kernel(PeerFlags peers, uint32_t* mine, int rank, int world, uint32_t epoch,
+                                    volatile uint32_t* err, unsigned long long timeout_ns) {
     const int p = threadIdx.x;
     if (p >= world) return;
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.f[p] + rank), "r"(epoch) : "memory");
-    const long long t0 = clock64();
-    for (;;) {
+    const unsigned long long t0 = global_ns();
+    for (uint32_t spins = 0;; ++spins) {
         uint32_t v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + p) : "memory");
         if (static_cast<int32_t>(v - epoch) >= 0) break;
-        if (clock64() - t0 > 40000000000LL) __trap();
+        if ((spins & 1023u) == 1023u) {
+            if (*err != 0u) break;
+            if (global_ns() - t0 > timeout_ns) {
+                *err = K5_DIST_ERR_BARRIER;
+                __threadfence_system();
+                break;
+            }
+        }
     }
 }
 
@@ -156,6 +173,10 @@ struct Engine {
         cudaEvent_t ev_kv = nullptr;
         cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // the pushes out of kv[buf] have read their source
         bool copied_valid[2] = {false, false};
+        // time-out reporting of the cross-GPU waits (dist_barrier_kernel, the slab wait of the attention producer)
+        uint32_t* err_host = nullptr;     // cudaHostAlloc(mapped): 0 = fine, else K5_DIST_ERR_*
+        uint32_t* err_dev = nullptr;      // the same word as the device sees it
+        unsigned long long timeout_ns = 600ull * 1000000000ull;
     } dist;
     int f0 = 0, Tl = 0, tok0 = 0, Sl = 0;
     // test hook (K5_DEBUG_KV_ORDER=<world>, read at set_grid): a single engine walks the KV tiles of the dense visual
@@ -184,6 +205,7 @@ struct Engine {
         return K5_OK;
     }
     ~Engine() {
+        if (dist.err_host) cudaFreeHost(dist.err_host);
         if (dist.copy_st) cudaStreamDestroy(dist.copy_st);
         if (dist.ev_kv) cudaEventDestroy(dist.ev_kv);
         for (cudaEvent_t ev : dist.ev_copied)
@@ -637,6 +659,15 @@ int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
     e->dist.rank = rank;
     e->dist.world = world;
     e->dist.on = world > 1;
+    if (!e->dist.err_host) {
+        K5_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->dist.err_host), sizeof(uint32_t), cudaHostAllocMapped));
+        *e->dist.err_host = 0;
+        K5_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->dist.err_dev), e->dist.err_host, 0));
+    }
+    if (const char* to = getenv("K5_DIST_TIMEOUT_S")) {
+        const double sec = atof(to);
+        if (sec > 0.0) e->dist.timeout_ns = static_cast<unsigned long long>(sec * 1e9);
+    }
     // Peers of the same process (the single-GPU tests drive several engines on one device) keep the scatter + barrier
     // form: an attention kernel that waits for a slab inside its producer would occupy the SMs its peer needs.
     bool cross = world > 1;
@@ -661,7 +692,8 @@ int engine_dist_barrier(Engine* e, cudaStream_t st) {
     for (int p = 0; p < MAX_PEERS; ++p) pf.f[p] = e->dist.peer_flags[p];
     ++e->dist.epoch;
     count_launch(1);
-    dist_barrier_kernel<<<1, 32, 0, st>>>(pf, e->dist.flags, e->dist.rank, e->dist.world, e->dist.epoch);
+    dist_barrier_kernel<<<1, 32, 0, st>>>(pf, e->dist.flags, e->dist.rank, e->dist.world, e->dist.epoch, e->dist.err_dev,
+                                          e->dist.timeout_ns);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }
@@ -797,6 +829,8 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
         K5_CHECK_CUDA(cudaEventRecord(d.ev_copied[buf], d.copy_st));
         d.copied_valid[buf] = true;
         slabs.flags = d.flags + FLAG_READY + buf * 8;
+        slabs.err = d.err_dev;
+        slabs.timeout_ns = d.timeout_ns;
         slabs.epoch = d.epoch;
         slabs.n = W_;
         slabs.first = r;
@@ -883,6 +917,12 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
                    float time, const k5_sparse* sp, bf16* out, cudaStream_t st, int mag_slot = -1, int mag_skip = 0) {
     K5_REQUIRE(e->finalized, "forward: call k5_engine_finalize first");
     K5_REQUIRE(e->grid_set, "forward: call k5_engine_set_grid first");
+    if (e->dist.on && e->dist.err_host && *static_cast<volatile uint32_t*>(e->dist.err_host) != 0u) {
+        set_last_error("temporal shard: a peer rank did not arrive within the time-out (K5_DIST_TIMEOUT_S) at " +
+                       std::string(*e->dist.err_host == K5_DIST_ERR_BARRIER ? "the K|V barrier" : "a K|V slab") +
+                       "; every result since then is invalid and the ranks are out of step - re-create the engines");
+        return K5_ERR_CUDA;
+    }
     K5_REQUIRE(x && text && pooled && out, "forward: null tensor");
     K5_REQUIRE(Cx == e->Cin || Cx == e->c.in_visual_dim, "forward: x must have model-input or latent channel count");
     K5_REQUIRE(L > 0 && L <= e->c.max_text_tokens, "forward: text length out of range");
@@ -985,8 +1025,12 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
     return K5_OK;
 }
 
+// skip_schedule (MagCache, optional): [num_steps * 2] bytes, entry 2 i + slot != 0 = forward `slot` (0 conditional,
+// 1 unconditional) of step i replaces its visual blocks by the cached residual (magcache_utils.py:64-88).  The decisions
+// depend on the calibrated magnitude ratios only, never on data, so the host computes the whole schedule up front.
 int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, const bf16* text, int L, const bf16* pooled,
-                  const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st) {
+                  const bf16* ntext, int Ln, const bf16* npooled, const k5_sparse* sp, cudaStream_t st,
+                  const uint8_t* skip_schedule) {
     K5_REQUIRE(e->grid_set, "sample: call k5_engine_set_grid first");
     K5_REQUIRE(num_steps > 0 && img, "sample: bad arguments");
     const bool cfg = fabsf(w - 1.0f) > 1e-6f;
@@ -1006,10 +1050,13 @@ int engine_sample(Engine* e, float* img, int num_steps, float w, float sched, co
     }
     for (int i = 0; i < num_steps; ++i) {
         const float t = ts[i], dt = ts[i + 1] - ts[i];
-        K5_TRY(engine_forward(e, img, e->c.in_visual_dim, text, L, nullptr, pooled, t * 1000.0f, sp, e->v_c, st));
+        const bool mag = skip_schedule != nullptr;
+        K5_TRY(engine_forward(e, img, e->c.in_visual_dim, text, L, nullptr, pooled, t * 1000.0f, sp, e->v_c, st, mag ? 0 : -1,
+                              mag ? skip_schedule[2 * i] : 0));
         const bf16* v = e->v_c + off;
         if (cfg) {
-            K5_TRY(engine_forward(e, img, e->c.in_visual_dim, ntext, Ln, nullptr, npooled, t * 1000.0f, sp, e->v_u, st));
+            K5_TRY(engine_forward(e, img, e->c.in_visual_dim, ntext, Ln, nullptr, npooled, t * 1000.0f, sp, e->v_u, st,
+                                  mag ? 1 : -1, mag ? skip_schedule[2 * i + 1] : 0));
             count_launch(1);
             K5_TRY(cfg_combine(e->v_c + off, e->v_u + off, w, e->v_c + off, n, st));
         }

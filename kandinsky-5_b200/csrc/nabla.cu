@@ -6,9 +6,9 @@
 //   map[i, :] = softmax_fp32( bf16(qa_i . ka_j) / sqrt(64) )
 //   sort ascending, cumulative sum, keep the entries whose cumulative mass is >= 1 - P, OR the STA mask
 //   kv_nb = number kept, kv_inds = their block ids
-// Here: one kernel pools q and k, one kernel does a whole map row per thread block (scores, softmax, a radix search
-// for the probability of the cut entry instead of a sort, OR with STA, ordered compaction).  The map is never
-// written to HBM (the reference materialises [1,28,1464,1464] fp32 = 240 MB per layer).
+// Here: one kernel pools q and k, one kernel does eight map rows per thread block (scores against the pooled keys
+// shared by the eight rows, then one warp per row: softmax, a radix search for the probability of the cut entry instead
+// of a sort, OR with STA, ordered compaction).  The map is never written to HBM (the reference materialises [1,28,1464,1464] fp32 = 240 MB per layer).
 #include "nabla.h"
 #include "ptx.cuh"
 
@@ -18,8 +18,8 @@ namespace {
 
 constexpr int NB_MAX = 2048;          // max 64-token blocks per sequence (131 072 tokens)
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_WARPS = SEL_THREADS / 32;
-constexpr int EPT = NB_MAX / SEL_THREADS;      // map entries per thread (entry j = tid + e * SEL_THREADS)
+constexpr int SEL_ROWS = SEL_THREADS / 32;     // map rows (query blocks) per thread block: one per warp
+constexpr int EPL = NB_MAX / 32;               // map entries per lane (entry j = lane + 32 e)
 
 // pooled[b, c] = bf16( mean over the 64 rows of block b of x[:, c] )
 __global__ void pool64_kernel(const bf16* __restrict__ x, int ld, int cols, bf16* __restrict__ pooled) {
@@ -33,129 +33,116 @@ __global__ void pool64_kernel(const bf16* __restrict__ x, int ld, int cols, bf16
     }
 }
 
-// Deterministic block reduction (warp tree, then the warps in order); every thread gets the result.
-__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float u = __shfl_xor_sync(0xffffffffu, v, o);
-        v = is_max ? fmaxf(v, u) : v + u;
-    }
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float r = red[0];
-#pragma unroll
-    for (int w = 1; w < SEL_WARPS; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
-    return r;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
-// One (head, query block) row of the map per thread block.
+// Eight map rows (query blocks i0 .. i0 + 7 of one head) per thread block.
+//
+// Phase 1, all 256 threads: the scores of the eight rows against every pooled key.  A key row (128 B) is fetched once
+// and used for all eight query rows, so the pooled K of a head is read from L2 once per EIGHT map rows (one map row per
+// block re-read it for every row: 7.7 GB of L2 traffic per layer at the 10 s size, which bounded that kernel).
+// Phase 2, one warp per row, no block-wide synchronisation: fp32 softmax, the cut, OR with the STA row, compaction.
 //
 // The reference sorts the row ascending, takes the cumulative sum and keeps every entry from the first position whose
 // cumulative mass reaches 1 - P.  Only that cut matters, not the order, so no sort is done: with A(v) = sum of the
 // probabilities whose bit pattern is below v (non-negative floats order like their bit patterns), the probability
-// tau of the cut entry is the LARGEST pattern with A(tau) < 1 - P.  tau is built four bits at a time (eight rounds, each
-// evaluating the 15 candidates of the next hex digit with one block reduction); entries above tau are kept, entries
+// tau of the cut entry is the LARGEST pattern with A(tau) < 1 - P.  tau is built bit by bit from the top (31 rounds, each
+// one masked sum over the row reduced with warp shuffles); entries above tau are kept, entries
 // below are dropped, and of the c entries equal to tau (frequent: the scores are bf16) the first m in index order are
 // dropped - the tie order of the reference's stable sort - where m is the number of copies of tau that still fit
-// under 1 - P.  (A 2 048-wide bitonic sort + scan took 9.2 ms per layer at the 10 s size, 64 % of it in the sort.)
+// under 1 - P.  (History at the 10 s size, per layer: 2 048-wide bitonic sort + scan 9.4 ms; radix search with one map
+// row per block 3.25 ms; eight rows per block, hex digits 1.83 ms.)
 __global__ void __launch_bounds__(SEL_THREADS)
-nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int nbq, int nb, int heads, float need,
-                 const uint8_t* __restrict__ sta, int sta_row0, int32_t* __restrict__ kv_count,
-                 int32_t* __restrict__ kv_index, float* __restrict__ density_acc) {
-    __shared__ float qrow[64];
-    __shared__ float red[SEL_WARPS];
-    __shared__ float cand[SEL_WARPS][16];
-    __shared__ float total[16];
-    __shared__ int warp_counts[2][SEL_WARPS];
-    const int i = blockIdx.x, h = blockIdx.y;
+nabla_rows_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int nbq, int nb, int heads, float need,
+                  const uint8_t* __restrict__ sta, int sta_row0, int32_t* __restrict__ kv_count,
+                  int32_t* __restrict__ kv_index, float* __restrict__ density_acc) {
+    extern __shared__ float sm[];
+    float* qrows = sm;                          // [SEL_ROWS][64]
+    float* sc = sm + SEL_ROWS * 64;             // [SEL_ROWS][nb]
+    const int i0 = blockIdx.x * SEL_ROWS, h = blockIdx.y;
     const int cols = heads * 64;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    if (tid < 64) qrow[tid] = __bfloat162float(qa[static_cast<size_t>(i) * cols + h * 64 + tid]);
+    for (int t = tid; t < SEL_ROWS * 64; t += SEL_THREADS) {
+        const int r = t >> 6;
+        qrows[t] = (i0 + r < nbq) ? __bfloat162float(qa[static_cast<size_t>(i0 + r) * cols + h * 64 + (t & 63)]) : 0.f;
+    }
     __syncthreads();
-    // scores: bf16(q . k) / 8 kept in bf16 (the reference's matmul and division run in bf16), then fp32 softmax
-    float pv[EPT];
-    float mx = -INFINITY;
+    // ---- phase 1: scores, bf16(q . k) / 8 kept in bf16 (the reference's matmul and division run in bf16)
+    for (int j = tid; j < nb; j += SEL_THREADS) {
+        const uint4* kr = reinterpret_cast<const uint4*>(ka + static_cast<size_t>(j) * cols + h * 64);
+        float kf[64];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int j = tid + e * SEL_THREADS;
-        float s = -INFINITY;
-        if (j < nb) {
-            const uint4* kr = reinterpret_cast<const uint4*>(ka + static_cast<size_t>(j) * cols + h * 64);
+        for (int v = 0; v < 8; ++v) {
+            const uint4 u = __ldg(kr + v);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                kf[8 * v + 2 * t] = bf16_lo(w[t]);
+                kf[8 * v + 2 * t + 1] = bf16_hi(w[t]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SEL_ROWS; ++r) {
+            const float4* q4 = reinterpret_cast<const float4*>(qrows + r * 64);
             float acc = 0.f;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const uint4 u = __ldg(kr + v);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    acc = fmaf(qrow[8 * v + 2 * t], bf16_lo(w[t]), acc);
-                    acc = fmaf(qrow[8 * v + 2 * t + 1], bf16_hi(w[t]), acc);
-                }
+            for (int d = 0; d < 16; ++d) {
+                const float4 q = q4[d];          // same address in every lane: a broadcast
+                acc = fmaf(q.x, kf[4 * d], acc);
+                acc = fmaf(q.y, kf[4 * d + 1], acc);
+                acc = fmaf(q.z, kf[4 * d + 2], acc);
+                acc = fmaf(q.w, kf[4 * d + 3], acc);
             }
-            s = bf16_round(bf16_round(acc) * 0.125f);
+            sc[r * nb + j] = bf16_round(bf16_round(acc) * 0.125f);
         }
-        pv[e] = s;
-        mx = fmaxf(mx, s);
     }
-    mx = block_reduce(mx, red, true);
+    __syncthreads();
+    // ---- phase 2: one warp per map row
+    const int i = i0 + warp;
+    if (i >= nbq) return;
+    const float* srow = sc + warp * nb;
+    float pv[EPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        const int j = lane + 32 * e;
+        pv[e] = j < nb ? srow[j] : -INFINITY;
+        mx = fmaxf(mx, pv[e]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        pv[e] = (tid + e * SEL_THREADS < nb) ? expf(pv[e] - mx) : 0.f;
+    for (int e = 0; e < EPL; ++e) {
+        pv[e] = (lane + 32 * e < nb) ? expf(pv[e] - mx) : 0.f;
         sum += pv[e];
     }
-    sum = block_reduce(sum, red, false);
+    sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    uint32_t bits[EPT];                       // bit patterns of the probabilities; entries past nb never match anything
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        pv[e] *= inv;
-        bits[e] = __float_as_uint(pv[e]);
-    }
-    // ---- tau: the largest pattern v with A(v) < need, one hex digit per round
+    for (int e = 0; e < EPL; ++e) pv[e] *= inv;          // entries past nb are +0.0: never above a positive tau, never a tie
+    // ---- tau: the largest pattern v with A(v) < need, one bit per round (A is monotone in v, so the greedy choice of
+    // every bit from the top is exact; 31 rounds of one compare + one predicated add per entry cost a quarter of
+    // eight rounds with the 15 candidates of a hex digit)
     uint32_t v = 0;
     float a_v = 0.f;                          // A(v)
-    for (int shift = 28; shift >= 0; shift -= 4) {
-        const uint32_t hv = v >> shift;       // low digit is 0
-        float part[15];
+    for (int bit = 30; bit >= 0; --bit) {     // probabilities are non-negative: the sign bit stays 0
+        const uint32_t c = v | (1u << bit);
+        float part = 0.f;
 #pragma unroll
-        for (int d = 0; d < 15; ++d) part[d] = 0.f;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-            if (tid + e * SEL_THREADS < nb) {
-                const uint32_t hb = bits[e] >> shift;
-#pragma unroll
-                for (int d = 0; d < 15; ++d)
-                    if (hb < hv + d + 1) part[d] += pv[e];          // below candidate v | ((d + 1) << shift)
+        for (int e = 0; e < EPL; ++e) {
+            if (32 * e < nb) {                                          // warp-uniform; entries past nb hold +0.0
+                if (__float_as_uint(pv[e]) < c) part += pv[e];
             }
         }
-#pragma unroll
-        for (int d = 0; d < 15; ++d) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part[d] += __shfl_xor_sync(0xffffffffu, part[d], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int d = 0; d < 15; ++d) cand[warp][d] = part[d];
-        }
-        __syncthreads();
-        if (tid < 15) {
-            float t = cand[0][tid];
-#pragma unroll
-            for (int w = 1; w < SEL_WARPS; ++w) t += cand[w][tid];
-            total[tid] = t;
-        }
-        __syncthreads();
-        int best = 0;                         // largest digit whose candidate still has A < need (A is monotone)
-#pragma unroll
-        for (int d = 0; d < 15; ++d)
-            if (total[d] < need) best = d + 1;
-        if (best > 0) {
-            v |= static_cast<uint32_t>(best) << shift;
-            a_v = total[best - 1];
+        const float t = warp_sum(part);
+        if (t < need) {
+            v = c;
+            a_v = t;
         }
     }
     // ---- ties: entries equal to tau, the first m of them in index order are dropped
@@ -171,39 +158,26 @@ nabla_row_kernel(const bf16* __restrict__ qa, const bf16* __restrict__ ka, int n
     // ---- keep flags, OR with the STA row, ordered compaction (ascending block id)
     int32_t* out = kv_index + (static_cast<size_t>(h) * nbq + i) * nb;
     const uint8_t* sta_row = sta ? sta + static_cast<size_t>(sta_row0 + i) * nb : nullptr;
+    const unsigned lt = (1u << lane) - 1u;
     int base = 0, tie_base = 0;
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int j = tid + e * SEL_THREADS;
-        if (e * SEL_THREADS >= nb) break;                          // block-uniform
-        const bool in = j < nb;
-        const bool tie = in && bits[e] == v;
-        const unsigned bal_t = __ballot_sync(0xffffffffu, tie);
-        if (lane == 0) warp_counts[0][warp] = __popc(bal_t);
-        __syncthreads();
-        int pre_t = 0, tot_t = 0;
-#pragma unroll
-        for (int w = 0; w < SEL_WARPS; ++w) {
-            if (w < warp) pre_t += warp_counts[0][w];
-            tot_t += warp_counts[0][w];
+    for (int e = 0; e < EPL; ++e) {
+        if (32 * e < nb) {                                              // warp-uniform
+            const int j = lane + 32 * e;
+            const bool in = j < nb;
+            const uint32_t bits = __float_as_uint(pv[e]);
+            const bool tie = in && bits == v;
+            const unsigned bal_t = __ballot_sync(0xffffffffu, tie);
+            const int rank = tie_base + __popc(bal_t & lt);
+            tie_base += __popc(bal_t);
+            bool k1 = in && (bits > v || (tie && rank >= m));
+            if (in && sta_row && sta_row[j]) k1 = true;
+            const unsigned bal = __ballot_sync(0xffffffffu, k1);
+            if (k1) out[base + __popc(bal & lt)] = j;
+            base += __popc(bal);
         }
-        const int rank = tie_base + pre_t + __popc(bal_t & ((1u << lane) - 1u));
-        tie_base += tot_t;
-        bool k1 = in && (bits[e] > v || (tie && rank >= m));
-        if (in && sta_row && sta_row[j]) k1 = true;
-        const unsigned bal = __ballot_sync(0xffffffffu, k1);
-        if (lane == 0) warp_counts[1][warp] = __popc(bal);
-        __syncthreads();
-        int pre = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < SEL_WARPS; ++w) {
-            if (w < warp) pre += warp_counts[1][w];
-            tot += warp_counts[1][w];
-        }
-        if (k1) out[base + pre + __popc(bal & ((1u << lane) - 1u))] = j;
-        base += tot;
     }
-    if (tid == 0) {
+    if (lane == 0) {
         kv_count[static_cast<size_t>(h) * nbq + i] = base;
         if (density_acc) {
             atomicAdd(density_acc, static_cast<float>(base));
@@ -244,8 +218,20 @@ int nabla_select(const bf16* q, int ldq, int Sq, const bf16* k, int ldk, int Sk,
     // the reference compares against the Python double 1 - P; undo the float round trip of P first
     const double Pd = nearbyint(static_cast<double>(P) * 1e6) / 1e6;
     const float need = static_cast<float>(1.0 - Pd);
-    nabla_row_kernel<<<dim3(nbq, heads), SEL_THREADS, 0, st>>>(qa, ka, nbq, nbk, heads, need, sta, sta_row0, kv_count, kv_index,
-                                                               density_acc);
+    const size_t smem = (static_cast<size_t>(SEL_ROWS) * 64 + static_cast<size_t>(SEL_ROWS) * nbk) * sizeof(float);
+    {
+        static PerDevice<int> pd;                 // > 48 KB of dynamic shared memory needs the opt-in, per device
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lk(pd.m);
+        if (!pd.set[dev]) {
+            K5_CHECK_CUDA(cudaFuncSetAttribute(nabla_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>((SEL_ROWS * 64 + SEL_ROWS * NB_MAX) * sizeof(float))));
+            pd.set[dev] = true;
+        }
+    }
+    nabla_rows_kernel<<<dim3((nbq + SEL_ROWS - 1) / SEL_ROWS, heads), SEL_THREADS, smem, st>>>(qa, ka, nbq, nbk, heads, need, sta,
+                                                                                                sta_row0, kv_count, kv_index,
+                                                                                                density_acc);
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;
 }

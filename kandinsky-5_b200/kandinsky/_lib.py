@@ -48,6 +48,8 @@ SIGNATURES = {
                                         POINTER(K5Sparse), c_void_p, c_int, c_int, c_void_p]),
     "k5_sample": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int,
                           c_void_p, POINTER(K5Sparse), c_void_p]),
+    "k5_sample_magcache": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                   c_void_p, POINTER(K5Sparse), c_void_p, c_void_p]),
     "k5_engine_attention_timing": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
     "k5_dist_export": (c_int, [c_void_p, c_void_p]),
     "k5_dist_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),

@@ -102,7 +102,7 @@ def generate(model, device, shape, num_steps, text_embeds, null_text_embeds, vis
     scale_factor = _get(conf, "metrics.scale_factor")
     arange_pos = (list(text_rope_pos.tolist()) == list(range(len(text_rope_pos)))
                   and list(null_text_rope_pos.tolist()) == list(range(len(null_text_rope_pos))))
-    if hasattr(model, "_engine") and arange_pos and getattr(model, "_magcache", None) is None:
+    if hasattr(model, "_engine") and arange_pos:
         # whole loop on the device
         T, H, W, _ = img.shape
         fractal = bool(sparse_params["to_fractal"]) if sparse_params is not None else False
@@ -114,9 +114,21 @@ def generate(model, device, shape, num_steps, text_embeds, null_text_embeds, vis
             ntext = null_text_embeds["text_embeds"].to(device, torch.bfloat16).contiguous() if cfg else None
             npooled = null_text_embeds["pooled_embed"].to(device, torch.bfloat16).contiguous().view(-1) if cfg else None
             sp = model._sparse_struct(sparse_params)
-            check(lib().k5_sample(model._engine, ptr(img), int(num_steps), float(guidance_weight), float(scheduler_scale),
-                                  ptr(text), text.shape[0], ptr(pooled), ptr(ntext), 0 if ntext is None else ntext.shape[0],
-                                  ptr(npooled), ctypes.byref(sp) if sp is not None else None, stream_ptr()))
+            args = (model._engine, ptr(img), int(num_steps), float(guidance_weight), float(scheduler_scale), ptr(text),
+                    text.shape[0], ptr(pooled), ptr(ntext), 0 if ntext is None else ntext.shape[0], ptr(npooled),
+                    ctypes.byref(sp) if sp is not None else None)
+            mag = getattr(model, "_magcache", None)
+            if mag is None:
+                check(lib().k5_sample(*args, stream_ptr()))
+            else:
+                # the skip decisions are host arithmetic on the calibrated ratios (magcache_utils.py:64-80): the state
+                # machine is stepped once per forward the loop will run, in the loop's order, before the loop starts
+                sched = (ctypes.c_uint8 * (2 * int(num_steps)))()
+                for i in range(int(num_steps)):
+                    for _ in range(2 if cfg else 1):
+                        slot, skip = mag.next()
+                        sched[2 * i + slot] = 1 if skip else 0
+                check(lib().k5_sample_magcache(*args, sched, stream_ptr()))
         return gather_frames(model, img)
     # generic path: same loop as the reference, one engine forward per call
     ts = timesteps(num_steps, scheduler_scale, device)

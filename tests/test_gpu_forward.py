@@ -171,3 +171,19 @@ def test_magcache_sampler_matches_reference_golden():
     print(f"magcache sampler: engine-vs-reference {err:.2e}, {sum(rec['skipped'])} of {len(decisions)} forwards skipped")
     assert err < 2e-2
     assert model._magcache.cnt == 0                                    # the schedule wrapped: ready for the next sample
+    # the device loop (k5_sample_magcache, taken above) against the reference's own loop shape: one get_velocity per
+    # step through the per-forward entry point (k5_dit_forward_magcache), Euler update in torch (generation_utils.py:105-128)
+    from kandinsky.generation_utils import get_velocity, timesteps
+
+    model._magcache.next = real_next
+    model._magcache.reset()
+    ts = timesteps(rec["steps"], rec["scheduler_scale"], "cuda")
+    x = img.cuda().clone()
+    for t, dt in zip(ts[:-1], torch.diff(ts)):
+        inp = torch.cat([x, torch.zeros_like(x), torch.zeros([*x.shape[:-1], 1], device="cuda")], dim=-1) if model.visual_cond else x
+        v = get_velocity(model, inp, t.unsqueeze(0), te, nte, pos, torch.arange(L), torch.arange(Ln), rec["guidance_weight"],
+                         conf, sparse_params=None)
+        x = x + dt * v
+    # (not bit-equal: torch's linspace / schedule arithmetic and the C++ restatement may differ in the last ulp of t)
+    print(f"magcache: device loop vs per-forward loop {rel_l2(out, x):.2e}, per-forward loop vs reference {rel_l2(x, rec['out']):.2e}")
+    assert rel_l2(x, rec["out"]) < 2e-2 and rel_l2(out, x) < 2e-2

@@ -139,6 +139,58 @@ def test_sharded_sampler_with_cfg_matches_single_engine():
         assert torch.equal(imgs[r][other], noise[other])          # frames of other ranks are left untouched
 
 
+def test_sharded_magcache_sampler_matches_single_engine():
+    """k5_sample_magcache on a 2-way shard: the residual caches hold each rank's own rows, the skip schedule is the
+    same host array on every rank, and the frames stay bit-identical to the single-engine run (which differs from the
+    plain sampler, i.e. the skips really happened)."""
+    from kandinsky._lib import check, lib, ptr
+    from kandinsky.models.parallelize import frame_partition
+
+    rec = torch.load(os.path.join(GOLD, "tiny_sampler_cfg.pt"), weights_only=False)
+    cfg = rec["cfg"]
+    T, H, W, L, Ln = rec["T"], rec["H"], rec["W"], rec["L"], rec["Ln"]
+    if T < 2:
+        pytest.skip("golden sampler case has a single frame")
+    steps = max(int(rec["steps"]), 4)
+    full, ranks = _models(cfg, T * (H // 2) * (W // 2), 2)
+    g = torch.Generator().manual_seed(1)
+    noise = torch.randn(T, H, W, 16, generator=g).cuda()
+    text = torch.randn(L, 3584, generator=g).to(torch.bfloat16).cuda()
+    pooled = torch.randn(768, generator=g).to(torch.bfloat16).cuda()
+    ntext = torch.randn(Ln, 3584, generator=g).to(torch.bfloat16).cuda()
+    npooled = torch.randn(768, generator=g).to(torch.bfloat16).cuda()
+    pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+    sched = (ctypes.c_uint8 * (2 * steps))(*[1 if (i // 2) % 2 == 1 else 0 for i in range(2 * steps)])   # every other step
+
+    def run(m, img, stream, schedule):
+        m.set_grid((T, H, W), pos, rec["scale_factor"], False)
+        args = (m._engine, ptr(img), steps, float(rec["guidance_weight"]), float(rec["scheduler_scale"]), ptr(text), L,
+                ptr(pooled), ptr(ntext), Ln, ptr(npooled), None)
+        with torch.cuda.stream(stream):
+            if schedule is None:
+                check(lib().k5_sample(*args, ctypes.c_void_p(stream.cuda_stream)))
+            else:
+                check(lib().k5_sample_magcache(*args, schedule, ctypes.c_void_p(stream.cuda_stream)))
+
+    ref, plain = noise.clone(), noise.clone()
+    run(full, ref, torch.cuda.current_stream(), sched)
+    run(full, plain, torch.cuda.current_stream(), None)
+    torch.cuda.synchronize()
+    assert not torch.equal(ref, plain)
+    imgs = [noise.clone() for _ in ranks]
+    streams = [torch.cuda.Stream() for _ in ranks]
+    torch.cuda.synchronize()
+    for m, im, st in zip(ranks, imgs, streams):
+        run(m, im, st, sched)
+    torch.cuda.synchronize()
+    for r, (f0, n) in enumerate(frame_partition(T, 2)):
+        assert torch.equal(imgs[r][f0:f0 + n], ref[f0:f0 + n])
+    bad = (ctypes.c_uint8 * (2 * steps))(*([1] * (2 * steps)))           # a skip before anything was cached
+    fresh, _ = _models(cfg, T * (H // 2) * (W // 2), 1)
+    with pytest.raises(ValueError):
+        run(fresh, noise.clone(), torch.cuda.current_stream(), bad)
+
+
 def test_dist_init_rejects_bad_arguments():
     rec = torch.load(os.path.join(GOLD, "cfg1_block_1x8x8.pt"), weights_only=False)
     from kandinsky.models.dit import DiffusionTransformer3D
