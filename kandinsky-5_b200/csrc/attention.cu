@@ -151,15 +151,14 @@ __device__ __forceinline__ void exp2_poly2_nc(float x0, float x1, float& p0, flo
     p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
     p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
 }
-// Dense BOUNDED kernel, tuning: pairs q with q % K5_ATTN_POLY_MOD == K5_ATTN_POLY_AT take the polynomial (0 = none)
+// Dense BOUNDED kernel: pair q (of the 64 per tile and thread) takes the polynomial when bit (q mod 16) of
+// K5_ATTN_POLY_MASK is set (0 = none).  Bits 0, 8 and 12 are left alone: pairs 16 / 32 / 48 gate the s_free arrive, pairs
+// 56 and 12 carry the barrier probes.
 // Measured (isolated, S = 47 616, two boxes, gpurun_out/r2_poly_nc.log): none 18.31 / 18.35 ms, every 8th 17.96 / 18.06,
 // every 6th 17.94 / 17.96, every 5th 18.01 / 18.02, every 4th 17.84 / 17.78 (pair 1 of 4) and 17.90 / 17.81 (pair 3 of 4);
 // with the clamp of the general path every 4th gave 17.96 / 18.11 and every 3rd 18.53 / 18.61 (slower than none).
-#ifndef K5_ATTN_POLY_MOD
-#define K5_ATTN_POLY_MOD 4
-#endif
-#ifndef K5_ATTN_POLY_AT
-#define K5_ATTN_POLY_AT 1
+#ifndef K5_ATTN_POLY_MASK
+#define K5_ATTN_POLY_MASK 0x2222
 #endif
 
 // NPOLY of every 8 element pairs take the polynomial path, the rest the MUFU.
@@ -178,7 +177,13 @@ __device__ __forceinline__ void exp2_poly2_nc(float x0, float x1, float& p0, flo
 // wait on the same barriers, so they are not independent streams: 19.1 against 18.7 ms) but block-sparse attention does:
 // a warp then owns exactly one 64 x 64 block of the tile and skips all work for a block that is not selected
 // (5.5 / 26.3 / 47.6 ms against 6.4 / 30.4 / 57.3 at densities 0.05 / 0.14 / 0.33, profiles/r2_attention.md).
-template <bool SPARSE, int NPOLY, bool BOUNDED, bool W16 = false>
+// PAIR (dense only): the kernel runs as thread-block clusters of two CTAs that work on adjacent query items of the
+// SAME head, i.e. on the same sequence of K / V tiles.  Each producer fetches one 64-row half of every K and V tile and
+// TMA-multicasts it into both CTAs' rings, so a tile crosses the L2 -> SM fabric once per pair instead of once per CTA
+// (148 CTAs x 12 MB of K|V per head otherwise).  A ring stage is handed back when the issuers of BOTH CTAs are done with
+// it (their commits arrive on both CTAs' barriers).  Everything else - Q, TMEM, the softmax warps - is per CTA as before.
+// The kernel sits at the 1 kW power cap, so what the fabric does not burn comes back as clock.
+template <bool SPARSE, int NPOLY, bool BOUNDED, bool W16 = false, bool PAIR = false>
 __global__ void __launch_bounds__(W16 ? ATT_THREADS_B : ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -191,6 +196,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int warp = threadIdx.x >> 5;
     // softmax warps 0 .. NSW-1, then producer, issuer of query tile 0, TMEM allocator, issuer of query tile 1
     static_assert(!W16 || BOUNDED, "two threads per row need the fixed-offset softmax");
+    static_assert(!PAIR || !SPARSE, "CTA pairs share dense K / V streams only");
+    [[maybe_unused]] const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     constexpr int NSW = W16 ? 16 : 8;
     constexpr int W_PROD = NSW, W_ISS0 = NSW + 1, W_ALLOC = NSW + 2, W_ISS1 = NSW + 3;
     constexpr uint32_t SM_THREADS = NSW * 16;            // softmax threads per query tile
@@ -233,15 +240,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         for (int s = 0; s < KV_STAGES; ++s) {
             mbar_init(&B->k_full[s], 1);
-            mbar_init(&B->k_empty[s], 2);            // both issuers commit on a stage before it is refilled
+            mbar_init(&B->k_empty[s], PAIR ? 4 : 2);  // both issuers (of both CTAs of a pair) commit on a stage before it is refilled
             mbar_init(&B->v_full[s], 1);
-            mbar_init(&B->v_empty[s], 2);
+            mbar_init(&B->v_empty[s], PAIR ? 4 : 2);
         }
         fence_barrier_init();
     }
     if (warp == W_ALLOC) tmem_alloc<512>(&B->tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = B->tmem_slot;
 
@@ -318,10 +326,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         uint8_t* sk = sKV + st * 2 * TILE_BYTES;
                         mbar_wait_lean_a<K5_ATTN_PROD_HINT>(smem_u32(&B->k_empty[st]), ph ^ 1);
                         mbar_expect_tx(&B->k_full[st], TILE_BYTES);
-                        tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, kv0);
+                        if constexpr (PAIR) {
+                            // this CTA's 64-row half (tmK / tmV have 64-row boxes here) goes to both rings; the other
+                            // half arrives from the peer's producer on the same barrier
+                            tma_load_2d_mc(sk + crank * (TILE_BYTES / 2), &tmK, &B->k_full[st], h * HD, kv0 + crank * (KT / 2), 0x3);
+                        } else {
+                            tma_load_2d(sk, &tmK, &B->k_full[st], h * HD, kv0);
+                        }
                         mbar_wait_lean_a<K5_ATTN_PROD_HINT>(smem_u32(&B->v_empty[st]), ph ^ 1);
                         mbar_expect_tx(&B->v_full[st], TILE_BYTES);
-                        tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, kv0);
+                        if constexpr (PAIR) {
+                            tma_load_2d_mc(sk + TILE_BYTES + crank * (TILE_BYTES / 2), &tmV, &B->v_full[st], h * HD,
+                                           kv0 + crank * (KT / 2), 0x3);
+                        } else {
+                            tma_load_2d(sk + TILE_BYTES, &tmV, &B->v_full[st], h * HD, kv0);
+                        }
                         if (++st == KV_STAGES) {
                             st = 0;
                             ph ^= 1;
@@ -370,7 +389,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) umma_ss(tS, qdesc0 + 2 * k, kdesc0 + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
                     umma_commit(&B->s_full[a]);
-                    umma_commit(&B->k_empty[kst]);
+                    if constexpr (PAIR) umma_commit_mc(&B->k_empty[kst], 0x3);
+                    else umma_commit(&B->k_empty[kst]);
                     if (last_of_item) umma_commit(&B->q_empty[a]);
                     if (++kst == KV_STAGES) {
                         kst = 0;
@@ -387,12 +407,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         for (int j = 0; j < nkv; ++j) {
                             mbar_wait(&B->k_full[kst], kph);
                             mbar_arrive(&B->k_empty[kst]);
+                            if constexpr (PAIR) mbar_arrive_cluster(&B->k_empty[kst], crank ^ 1u);
                             if (++kst == KV_STAGES) {
                                 kst = 0;
                                 kph ^= 1;
                             }
                             mbar_wait(&B->v_full[vst], vph);
                             mbar_arrive(&B->v_empty[vst]);
+                            if constexpr (PAIR) mbar_arrive_cluster(&B->v_empty[vst], crank ^ 1u);
                             if (++vst == KV_STAGES) {
                                 vst = 0;
                                 vph ^= 1;
@@ -475,7 +497,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         for (int k = 0; k < KT / 16; ++k)
                             umma_ts(tO, tP + k * 8, vdesc0 + 128 * k, idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
                         umma_commit(&B->pv_done[a]);
-                        umma_commit(&B->v_empty[vst]);
+                        if constexpr (PAIR) umma_commit_mc(&B->v_empty[vst], 0x3);
+                        else umma_commit(&B->v_empty[vst]);
                         K5_TRACE_ISSUER(5);
                         if (++vst == KV_STAGES) {
                             vst = 0;
@@ -599,7 +622,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                          x0, x1);
                             if ((q & 7) < NPOLY) {
                                 exp2_poly2(x0, x1, p0, p1);
-                            } else if (K5_ATTN_POLY_MOD > 0 && !SPARSE && (q % (K5_ATTN_POLY_MOD > 0 ? K5_ATTN_POLY_MOD : 1)) == K5_ATTN_POLY_AT) {
+                            } else if (!SPARSE && ((K5_ATTN_POLY_MASK >> (q & 15)) & 1)) {
                                 exp2_poly2_nc(x0, x1, p0, p1);
                             } else {
                                 p0 = fast_exp2(x0);
@@ -1024,6 +1047,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == W_ALLOC) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -1116,10 +1140,10 @@ int ensure_sparse_ws(AttnSparseWs& w, size_t items, size_t max_pairs) {
 
 namespace {
 
-constexpr int ATT_IMPL_DEFAULT = 2;      // 2 = two 128-row query tiles x 128-row KV tiles (this file), 4 = attention4.cu
 constexpr int ATT_NPOLY_DEFAULT = 0;
 constexpr float ATT_MAX_SCORE_BOUND = 60.f;   // log2 units
 constexpr int ATT_STAGGER_DEFAULT = 0;
+constexpr int ATT_PAIR_DEFAULT = 1;
 
 template <bool SPARSE, bool BOUNDED>
 void launch_kernel(int npoly, int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
@@ -1145,6 +1169,8 @@ int configure_set() {
     return K5_OK;
 }
 int configure_kernels() {
+    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false, 0, true, false, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     K5_TRY((configure_set<false, false>()));
     K5_TRY((configure_set<true, false>()));
     K5_TRY((configure_set<false, true>()));
@@ -1168,7 +1194,7 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
     K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
     K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
-    static int npoly = -1, stagger = 0, impl = ATT_IMPL_DEFAULT, split_tail = 1, use_bounded = 1;
+    static int npoly = -1, stagger = 0, split_tail = 1, use_bounded = 1;
     static std::mutex knob_mutex;
     static PerDevice<int> configured;
     {
@@ -1181,8 +1207,6 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     }
     std::lock_guard<std::mutex> knob_lock(knob_mutex);
     if (npoly < 0) {
-        if (const char* im = getenv("K5_ATTN_IMPL")) impl = atoi(im);
-        if (impl != 2 && impl != 4) impl = ATT_IMPL_DEFAULT;
         if (const char* sp = getenv("K5_ATTN_SPLIT_TAIL")) split_tail = atoi(sp) != 0;
         const char* sg = getenv("K5_ATTN_STAGGER");
         stagger = sg ? atoi(sg) : ATT_STAGGER_DEFAULT;
@@ -1215,7 +1239,7 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.slab_first = 0;
     for (int& t : p.slab_tile0) t = 0;
     if (slabs && slabs->n > 0) {     // flags == nullptr: the slab ORDER only (debug: single engine in a rank's order)
-        K5_REQUIRE(!sparse && impl == 2, "attention: the overlapped gather is implemented for the dense kernel");
+        K5_REQUIRE(!sparse, "attention: the overlapped gather is implemented for the dense kernel");
         K5_REQUIRE(slabs->n >= 1 && slabs->n <= 8 && slabs->first >= -1 && slabs->first < slabs->n && Sk % KT == 0 &&
                        (slabs->first >= 0 || slabs->flags == nullptr) &&
                        slabs->row0[0] == 0 && slabs->row0[slabs->n] == Sk,
@@ -1237,7 +1261,6 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     }
     // fixed-offset softmax only under a proven bound that keeps exp2 and the fp32 row sums far from overflow
     const bool bounded = use_bounded && score_bound > 0.f && score_bound <= ATT_MAX_SCORE_BOUND;
-    if (impl == 4) return attention_fwd_v4(Q, ldq, K, ldk, V, ldv, p, st, ws_in ? *ws_in : g_sparse_ws);
     const int n_qpairs = (Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * heads;
     const int grid = n_items < sm_count() ? n_items : sm_count();
@@ -1261,8 +1284,50 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         if (bounded) launch_kernel<true, true>(npoly, grid, tmQ, tmK, tmV, p, st);
         else launch_kernel<true, false>(npoly, grid, tmQ, tmK, tmV, p, st);
     } else {
-        if (bounded) launch_kernel<false, true>(npoly, grid, tmQ, tmK, tmV, p, st);
-        else launch_kernel<false, false>(npoly, grid, tmQ, tmK, tmV, p, st);
+        // CTA pairs sharing the K / V stream (see the kernel): adjacent items must belong to one head (even item count
+        // per head) and the grid must consist of whole pairs.  K5_ATTN_PAIR=0 restores single CTAs (A/B).
+        static int pair_env = -1;
+        if (pair_env < 0) {
+            const char* ev = getenv("K5_ATTN_PAIR");
+            pair_env = ev ? (atoi(ev) != 0) : ATT_PAIR_DEFAULT;
+        }
+        if (bounded && npoly == 0 && pair_env && n_qpairs % 2 == 0 && grid % 2 == 0) {
+            CUtensorMap tmK64, tmV64;
+            K5_TRY(make_tmap_2d_bf16(&tmK64, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT / 2));
+            K5_TRY(make_tmap_2d_bf16(&tmV64, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT / 2));
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / 2 * 2));
+            cfg.blockDim = dim3(ATT_THREADS);
+            cfg.dynamicSmemBytes = ATT_SMEM;
+            cfg.stream = st;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            static PerDevice<int> max_pairs;          // clusters that can be resident at once (pairs live inside a GPC)
+            int resident = 0;
+            {
+                const int dev = current_device();
+                std::lock_guard<std::mutex> lk(max_pairs.m);
+                if (!max_pairs.set[dev]) {
+                    int n_clusters = 0;
+                    K5_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n_clusters, attention_fwd_kernel<false, 0, true, false, true>, &cfg));
+                    K5_REQUIRE(n_clusters > 0, "attention: no CTA pair fits this device");
+                    max_pairs.v[dev] = n_clusters;
+                    max_pairs.set[dev] = true;
+                }
+                resident = 2 * max_pairs.v[dev];
+            }
+            cfg.gridDim = dim3(static_cast<unsigned>(grid < resident ? grid : resident));
+            K5_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attention_fwd_kernel<false, 0, true, false, true>, tmQ, tmK64, tmV64, p));
+        } else if (bounded) {
+            launch_kernel<false, true>(npoly, grid, tmQ, tmK, tmV, p, st);
+        } else {
+            launch_kernel<false, false>(npoly, grid, tmQ, tmK, tmV, p, st);
+        }
     }
     K5_CHECK_CUDA(cudaGetLastError());
     return K5_OK;

@@ -66,8 +66,5 @@ int attention_debug_trace(long long* buf);
 // Grows the pre-pass scratch to at least items x max_pairs entries.
 int ensure_sparse_ws(AttnSparseWs& w, size_t items, size_t max_pairs);
 
-// Software-pipelined softmax over 64-row KV tiles (attention4.cu, K5_ATTN_IMPL=4).
-int attention_fwd_v4(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, AttnParams p, cudaStream_t st,
-                     AttnSparseWs& ws);
 
 }  // namespace k5

@@ -21,15 +21,42 @@ constexpr int SEL_THREADS = 256;
 constexpr int SEL_ROWS = SEL_THREADS / 32;     // map rows (query blocks) per thread block: one per warp
 constexpr int EPL = NB_MAX / 32;               // map entries per lane (entry j = lane + 32 e)
 
-// pooled[b, c] = bf16( mean over the 64 rows of block b of x[:, c] )
-__global__ void pool64_kernel(const bf16* __restrict__ x, int ld, int cols, bf16* __restrict__ pooled) {
-    const int b = blockIdx.x;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-        float acc = 0.f;
-        const bf16* p = x + static_cast<size_t>(b) * 64 * ld + c;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) acc += __bfloat162float(p[static_cast<size_t>(r) * ld]);
-        pooled[static_cast<size_t>(b) * cols + c] = __float2bfloat16_rn(acc * (1.0f / 64.0f));
+// pooled[b, c] = bf16( mean over the 64 rows of block b of x[:, c] ), fp32 sum in row order.  One launch pools q
+// (blocks [0, nbq)) and k (blocks [nbq, nbq + nbk)); a thread owns 8 adjacent columns (16-byte loads, 8 rows in flight).
+__global__ void __launch_bounds__(256)
+pool64_kernel(const bf16* __restrict__ q, int ldq, int nbq, const bf16* __restrict__ k, int ldk, int cols,
+              bf16* __restrict__ qa, bf16* __restrict__ ka) {
+    const bool is_q = static_cast<int>(blockIdx.x) < nbq;
+    const int b = is_q ? blockIdx.x : blockIdx.x - nbq;
+    const bf16* x = is_q ? q : k;
+    const int ld = is_q ? ldq : ldk;
+    bf16* pooled = is_q ? qa : ka;
+    for (int c8 = threadIdx.x; c8 < cols / 8; c8 += blockDim.x) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const bf16* p = x + static_cast<size_t>(b) * 64 * ld + c8 * 8;
+#pragma unroll
+        for (int r0 = 0; r0 < 64; r0 += 8) {
+            uint4 u[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) u[r] = __ldg(reinterpret_cast<const uint4*>(p + static_cast<size_t>(r0 + r) * ld));
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    acc[2 * t] += bf16_lo(w[t]);
+                    acc[2 * t + 1] += bf16_hi(w[t]);
+                }
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0] * (1.0f / 64.0f), acc[1] * (1.0f / 64.0f));
+        o.y = pack_bf16x2(acc[2] * (1.0f / 64.0f), acc[3] * (1.0f / 64.0f));
+        o.z = pack_bf16x2(acc[4] * (1.0f / 64.0f), acc[5] * (1.0f / 64.0f));
+        o.w = pack_bf16x2(acc[6] * (1.0f / 64.0f), acc[7] * (1.0f / 64.0f));
+        *reinterpret_cast<uint4*>(pooled + static_cast<size_t>(b) * cols + c8 * 8) = o;
     }
 }
 
@@ -202,7 +229,7 @@ size_t nabla_workspace_floats(int S, int heads) {
     const size_t nb = S / 64;
     return static_cast<size_t>(heads) * nb * nb + 2 * nb * static_cast<size_t>(heads) * 64;
 }
-int nabla_select_launches() { return 3; }
+int nabla_select_launches() { return 2; }
 
 int nabla_select(const bf16* q, int ldq, int Sq, const bf16* k, int ldk, int Sk, int heads, float P, const uint8_t* sta,
                  int sta_row0, int32_t* kv_count, int32_t* kv_index, float* workspace, float* density_acc, cudaStream_t st) {
@@ -213,8 +240,9 @@ int nabla_select(const bf16* q, int ldq, int Sq, const bf16* k, int ldk, int Sk,
     const int cols = heads * 64;
     bf16* qa = reinterpret_cast<bf16*>(workspace);
     bf16* ka = qa + static_cast<size_t>(nbq) * cols;
-    pool64_kernel<<<nbq, 256, 0, st>>>(q, ldq, cols, qa);
-    pool64_kernel<<<nbk, 256, 0, st>>>(k, ldk, cols, ka);
+    K5_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "NABLA: q, k and the workspace must be 16-byte aligned");
+    pool64_kernel<<<nbq + nbk, 256, 0, st>>>(q, ldq, nbq, k, ldk, cols, qa, ka);
     // the reference compares against the Python double 1 - P; undo the float round trip of P first
     const double Pd = nearbyint(static_cast<double>(P) * 1e6) / 1e6;
     const float need = static_cast<float>(1.0 - Pd);

@@ -226,6 +226,15 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & K5_PEER_BIT_MASK) : "memory");
 }
 
+// Plain arrive on the barrier at the same offset in CTA `cta` of the cluster (mapa = map a shared::cta address there).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------- thread-block clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

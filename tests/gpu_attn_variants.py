@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the attention kernel variants on one B200 (not a pytest file).  The variant knobs (K5_ATTN_IMPL,
+"""A/B of the attention kernel variants on one B200 (not a pytest file).  The variant knobs (K5_ATTN_BOUNDED,
 K5_ATTN_SPLIT_TAIL, K5_ATTN_POLY, K5_ATTN_STAGGER) are read once per process, so every variant runs in its own subprocess: a correctness check
 against a torch fp32 restatement (dense with a ragged KV tail, cross-attention shape, block-sparse against the masked
 dense result) followed by the isolated-kernel timing at the 5 s size (S = 47 616, 28 heads).
@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "kandinsky-5_b200"))
 
-DEFAULT = ["v2=K5_ATTN_IMPL:2", "bounded=K5_VARIANT_BOUND:1", "bounded_poly1=K5_VARIANT_BOUND:1,K5_ATTN_POLY:1",
+DEFAULT = ["general=", "bounded=K5_VARIANT_BOUND:1", "bounded_poly1=K5_VARIANT_BOUND:1,K5_ATTN_POLY:1",
            "bounded_poly2=K5_VARIANT_BOUND:1,K5_ATTN_POLY:2"]
 # K5_VARIANT_BOUND=1: q and k are RMS-normalised per head (as the DiT does, nn.py:246-250) and the proven score bound
 # 8 * 8 / 8 * log2(e) * w_q * w_k is handed to k5_attention_bounded -> fixed-offset softmax kernel.

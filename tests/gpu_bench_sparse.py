@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Block-sparse (NABLA) attention timing at the 10 s size (S = 93 696 tokens = 1 464 blocks of 64, 28 heads) for block
 selections of different density: the STA window alone (wT = 11, wH = wW = 3 -> 4.8 %) and the window OR'ed with a random
-selection.  Prints the time per launch and the rate over the SELECTED blocks; K5_ATTN_IMPL picks the kernel.
+selection.  Prints the time per launch and the rate over the SELECTED blocks (K5_VARIANT_BOUND=1: the DiT's bounded kernel).
 Not a pytest file."""
 import os
 import sys
@@ -50,7 +50,7 @@ def main():
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / 4
         fl = 4.0 * S * S * D * rho
-        print(f"impl={os.environ.get('K5_ATTN_IMPL', 'default')} bounded={bound is not None} density {rho:.3f}: {ms:.2f} ms = {fl / ms / 1e9:.0f} TFLOP/s of the selected blocks", flush=True)
+        print(f"bounded={bound is not None} density {rho:.3f}: {ms:.2f} ms = {fl / ms / 1e9:.0f} TFLOP/s of the selected blocks", flush=True)
 
 
 if __name__ == "__main__":

@@ -6,5 +6,5 @@ run "" "bounded=K5_VARIANT_BOUND:1"
 run "" "bounded_stagger1100=K5_VARIANT_BOUND:1,K5_ATTN_STAGGER:1100"
 run "" "bounded_stagger1600=K5_VARIANT_BOUND:1,K5_ATTN_STAGGER:1600"
 run _pp "bounded_pp=K5_VARIANT_BOUND:1,K5_VARIANT_SAMPLE:1"
-run "" "v2=K5_ATTN_IMPL:2"
+run "" "general="
 cat $L

@@ -5,5 +5,5 @@ for v in "$@"; do
   [ "$v" = "-" ] && v=""
   K5_LIB_PATH=$PWD/kandinsky-5_b200/libk5$v.so timeout 100 python tests/gpu_attn_variants.py "bounded$v=K5_VARIANT_BOUND:1,K5_VARIANT_SAMPLE:1" >> $L 2>&1
 done
-K5_LIB_PATH=$PWD/kandinsky-5_b200/libk5.so timeout 300 python tests/gpu_attn_variants.py "v2=K5_ATTN_IMPL:2" >> $L 2>&1
+K5_LIB_PATH=$PWD/kandinsky-5_b200/libk5.so timeout 300 python tests/gpu_attn_variants.py "general=" >> $L 2>&1
 cat $L
