@@ -169,9 +169,15 @@ struct Engine {
         // overlapped all-gather (ranks in different processes): the projection writes the local slab only, copy
         // engines push it to the peers on `copy_st` while the attention kernel already runs on the local slab
         bool overlap = false;
-        cudaStream_t copy_st = nullptr;
+        // The pushes of a block go out in the order their consumers need them (rank r - 1 reads slab r first), round-robin
+        // over a few copy streams.  Measured on 8 ranks (44 MB slabs): ONE stream moves ~120 GB/s, so slab k lands at
+        // k x 0.36 ms against a need at k x 0.30 ms and the attention waits 0.45 ms per block; ONE STREAM PER PEER reaches
+        // ~350 GB/s in total but every slab lands at the same late moment (0.9 ms, wait 0.59 ms); three streams keep the
+        // order and triple the rate (K5_DIST_COPY_STREAMS = 1 .. 7).
+        int n_copy_st = 3;
+        cudaStream_t copy_st[MAX_PEERS] = {};
         cudaEvent_t ev_kv = nullptr;
-        cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // the pushes out of kv[buf] have read their source
+        cudaEvent_t ev_copied[2][MAX_PEERS] = {};        // the pushes out of kv[buf] on copy stream i have read their source
         bool copied_valid[2] = {false, false};
         // time-out reporting of the cross-GPU waits (dist_barrier_kernel, the slab wait of the attention producer)
         uint32_t* err_host = nullptr;     // cudaHostAlloc(mapped): 0 = fine, else K5_DIST_ERR_*
@@ -206,10 +212,12 @@ struct Engine {
     }
     ~Engine() {
         if (dist.err_host) cudaFreeHost(dist.err_host);
-        if (dist.copy_st) cudaStreamDestroy(dist.copy_st);
+        for (cudaStream_t cs : dist.copy_st)
+            if (cs) cudaStreamDestroy(cs);
         if (dist.ev_kv) cudaEventDestroy(dist.ev_kv);
-        for (cudaEvent_t ev : dist.ev_copied)
-            if (ev) cudaEventDestroy(ev);
+        for (auto& row : dist.ev_copied)
+            for (cudaEvent_t ev : row)
+                if (ev) cudaEventDestroy(ev);
         for (void* p : dist.opened) cudaIpcCloseMemHandle(p);
         if (dist.block) cudaFree(dist.block);
         for (auto& v : ev) cudaEventDestroy(v);
@@ -673,12 +681,21 @@ int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
     bool cross = world > 1;
     for (int p = 0; p < world; ++p)
         if (p != rank && hs[p].pid == static_cast<int64_t>(getpid())) cross = false;
-    if (const char* ov = getenv("K5_DIST_OVERLAP")) cross = cross && atoi(ov) != 0;
+    // Default: the all-gather fused into the QKV epilogue + one flag barrier.  The overlapped form (K5_DIST_OVERLAP=1) is
+    // bit-identical to a single engine walking the slabs in the owners' order and hides the transfer behind the attention,
+    // but measured no faster end to end on 2 and 8 GPUs (109.5 - 113 against 109.7 ms per step on 8):
+    // the time it takes out of the projection comes back as waiting inside the attention kernel.
+    const char* ov = getenv("K5_DIST_OVERLAP");
+    cross = cross && ov != nullptr && atoi(ov) != 0;
     e->dist.overlap = cross;
-    if (cross && !e->dist.copy_st) {
-        K5_CHECK_CUDA(cudaStreamCreateWithFlags(&e->dist.copy_st, cudaStreamNonBlocking));
+    if (cross && !e->dist.ev_kv) {
         K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->dist.ev_kv, cudaEventDisableTiming));
-        for (cudaEvent_t& ev : e->dist.ev_copied) K5_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (const char* ns = getenv("K5_DIST_COPY_STREAMS")) e->dist.n_copy_st = atoi(ns);
+        e->dist.n_copy_st = e->dist.n_copy_st < 1 ? 1 : (e->dist.n_copy_st > MAX_PEERS - 1 ? MAX_PEERS - 1 : e->dist.n_copy_st);
+        for (int i = 0; i < e->dist.n_copy_st; ++i) {
+            K5_CHECK_CUDA(cudaStreamCreateWithFlags(&e->dist.copy_st[i], cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->dist.ev_copied[b][i], cudaEventDisableTiming));
+        }
     }
     e->dist.epoch = 0;
     e->dist.buf = 0;
@@ -793,7 +810,8 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
             g.peers.n = 1;         // the projection writes this rank's slab of its OWN buffer only
             g.peers.dst[0] = e->dist.kv[buf];
             // ... which the copy engines may still be reading for the pushes of two blocks ago
-            if (e->dist.copied_valid[buf]) K5_CHECK_CUDA(cudaStreamWaitEvent(st, e->dist.ev_copied[buf], 0));
+            if (e->dist.copied_valid[buf])
+                for (int i = 0; i < e->dist.n_copy_st; ++i) K5_CHECK_CUDA(cudaStreamWaitEvent(st, e->dist.ev_copied[buf][i], 0));
         } else {
             // all-gather fused into the projection: the K | V columns of this rank's rows go straight from the GEMM
             // epilogue into every rank's [S, 2D] buffer over NVLink; one flag barrier, then attention over all of S
@@ -814,19 +832,18 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
         Engine::Dist& d = e->dist;
         const int W_ = d.world, r = d.rank;
         K5_CHECK_CUDA(cudaEventRecord(d.ev_kv, st));
-        K5_CHECK_CUDA(cudaStreamWaitEvent(d.copy_st, d.ev_kv, 0));
-        // a wrap-safe ">= epoch - 2" on every peer's DONE slot (stream memory operations: no SM needed, so they make
-        // progress while the persistent attention kernel holds every SM - a signalling KERNEL on a second stream may not)
-        if (d.epoch > 2)
-            for (int p = 0; p < W_; ++p)
-                if (p != r) K5_TRY(stream_wait_geq_u32(d.copy_st, d.flags + FLAG_DONE + p, d.epoch - 2));
         const size_t off = static_cast<size_t>(e->tok0) * 2 * D, bytes = static_cast<size_t>(e->Sl) * 2 * D * sizeof(bf16);
+        for (int i = 0; i < d.n_copy_st; ++i) K5_CHECK_CUDA(cudaStreamWaitEvent(d.copy_st[i], d.ev_kv, 0));
         for (int k = 1; k < W_; ++k) {
-            const int p = (r - k + W_) % W_;
-            K5_CHECK_CUDA(cudaMemcpyAsync(d.peer_kv[buf][p] + off, d.kv[buf] + off, bytes, cudaMemcpyDeviceToDevice, d.copy_st));
-            K5_TRY(stream_write_u32(d.copy_st, d.peer_flags[p] + FLAG_READY + buf * 8 + r, d.epoch));
+            const int p = (r - k + W_) % W_;          // rank r - 1 reads slab r right after its own: it is served first
+            cudaStream_t cs = d.copy_st[(k - 1) % d.n_copy_st];
+            // a wrap-safe ">= epoch - 2" on the destination's DONE slot (stream memory operations: no SM needed, so they
+            // make progress while the persistent attention kernel holds every SM - a signalling KERNEL on a second stream may not)
+            if (d.epoch > 2) K5_TRY(stream_wait_geq_u32(cs, d.flags + FLAG_DONE + p, d.epoch - 2));
+            K5_CHECK_CUDA(cudaMemcpyAsync(d.peer_kv[buf][p] + off, d.kv[buf] + off, bytes, cudaMemcpyDeviceToDevice, cs));
+            K5_TRY(stream_write_u32(cs, d.peer_flags[p] + FLAG_READY + buf * 8 + r, d.epoch));
         }
-        K5_CHECK_CUDA(cudaEventRecord(d.ev_copied[buf], d.copy_st));
+        for (int i = 0; i < d.n_copy_st; ++i) K5_CHECK_CUDA(cudaEventRecord(d.ev_copied[buf][i], d.copy_st[i]));
         d.copied_valid[buf] = true;
         slabs.flags = d.flags + FLAG_READY + buf * 8;
         slabs.err = d.err_dev;

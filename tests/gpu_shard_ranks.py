@@ -3,7 +3,7 @@
 `python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/gpu_shard_ranks.py`).
 Every rank runs the sharded forward and, on its own GPU, the single-engine forward of the same inputs; its frames
 must be BIT-IDENTICAL.  With the scatter + barrier form of the all-gather (K5_DIST_OVERLAP=0) both walk the KV tiles
-in natural order.  With the overlapped all-gather (default across processes) a rank walks the slabs starting at its
+in natural order.  With the overlapped all-gather (K5_DIST_OVERLAP=1, across processes) a rank walks the slabs starting at its
 own, so the single engine is told to walk them, for every query row, in the order of the rank owning that row
 (K5_DEBUG_KV_ORDER, csrc/engine.cu): any difference left would be a slab read before it arrived.  Also runs the device sampler with CFG and gathers the latent
 through generate()."""
@@ -46,7 +46,7 @@ def main():
     ntext = torch.randn(Ln, 3584, generator=g).to(torch.bfloat16).to(dev)
     npooled = torch.randn(1, 768, generator=g).to(torch.bfloat16).to(dev)
     pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
-    overlapped = os.environ.get("K5_DIST_OVERLAP") != "0"
+    overlapped = os.environ.get("K5_DIST_OVERLAP", "0") not in ("", "0")
     ref_nat = None
     if overlapped:
         ref_nat = full(img, text, pooled, 700.0, pos, torch.arange(L), scale_factor=(1.0, 2.0, 2.0)).clone()

@@ -1,0 +1,14 @@
+N=${1:-8}
+mkdir -p gpurun_out
+L=gpurun_out/r2_shard_${N}gpu_b.log
+: > $L
+K5_SHARD_VERBOSE=1 K5_DIST_OVERLAP=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/gpu_shard_ranks.py 2>&1 | grep -E "shard x|Error|error|Traceback" >> $L
+for ov in 1 0; do
+  K5_DIST_OVERLAP=$ov timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$ov bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_${N}gpu_b_ov$ov.json 2>> gpurun_out/r2_bench_${N}gpu_b.err
+  python - <<PY >> $L
+import json
+d=json.loads(open("gpurun_out/r2_bench_${N}gpu_b_ov$ov.json").read().strip().splitlines()[-1])
+print("overlap=$ov N=$N ms/step", d["ms_per_step"], "tokens/s", d["value"], "attn ms", d["roofline"]["avg_launch_ms"], "share", d["roofline"]["share_of_step"], "e2e ms", d["e2e"]["ms_per_step"])
+PY
+done
+cat $L
