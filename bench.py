@@ -538,6 +538,12 @@ def run_k5(args, wl):
     # ---- device-resident timing (value) -------------------------------------------------------------------
     sample(max(args.warmup, 3), noise)
     barrier()
+    # how long the HOST needs to enqueue one sampler step (the call returns before the device has run it): what a CUDA
+    # graph could save at most, reported beside the device time
+    t_h = time.perf_counter()
+    sample(1, noise)
+    host_enqueue_ms = (time.perf_counter() - t_h) * 1e3
+    barrier()
     import ctypes
 
     lib.k5_engine_attention_timing(model._engine, 1, None, None)
@@ -620,11 +626,16 @@ def run_k5(args, wl):
     sustained, burst, src = measured_peaks()
     flops_fwd = dit_flops(S, L, density)
     attn_flops = density * 4.0 * S_loc * S * 1792          # per launch on this rank: own query rows x all keys
-    traffic = None
+    # dram bytes per launch of the dominant kernel: from the committed ncu --set full capture of the same kernel at the same
+    # size (profiles/attention_traffic.json names the .ncu-rep); null when that report is not in the tree
+    traffic, traffic_src = None, "not measured in this run"
     tpath = os.path.join(ROOT, "profiles", "attention_traffic.json")
     if world == 1 and os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload)
+            tj = json.load(f)
+        if os.path.exists(os.path.join(ROOT, tj.get("_report", "missing"))):
+            traffic = tj.get(args.workload)
+            traffic_src = "ncu --set full capture " + tj["_report"] if traffic is not None else traffic_src
     att_avg_ms = att_ms.value / max(att_n.value, 1)
     achieved = attn_flops / (att_avg_ms * 1e-3) / 1e12 if att_n.value else None
     line = {
@@ -638,6 +649,7 @@ def run_k5(args, wl):
         "model_tflops_achieved": flops_fwd * fwd_per_step / (ms_step * 1e-3) / 1e12,
         "model_frac_of_sustained_peak": flops_fwd * fwd_per_step / (ms_step * 1e-3) / 1e12 / sustained,
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clk,
         "e2e": {"value": S * fwd_per_step / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -646,7 +658,8 @@ def run_k5(args, wl):
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                      "frac": (achieved / sustained) if achieved else None, "peak_source": f"{src} (sustained bf16 GEMM)",
                      "flops_per_launch": attn_flops, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n.value),
-                     "share_of_step": att_ms.value / ms_total if ms_total else None, "traffic": traffic},
+                     "share_of_step": att_ms.value / ms_total if ms_total else None, "traffic": traffic,
+                     "traffic_source": traffic_src},
     }
     if vae_info is not None:
         line["vae_decode"] = vae_info

@@ -8,3 +8,12 @@ export K5_VARIANT_NAME=ncu K5_VARIANT_BOUND=1 K5_VARIANT_NOCHECK=1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_fwd -s 9 -c 1 -f -o gpurun_out/r2_attention_final python tests/gpu_attn_variants.py > gpurun_out/r2_attention_final.log 2>&1
 tail -3 gpurun_out/r2_attention_final.log
 ls -la gpurun_out/r2_attention_final.ncu-rep
+unset K5_VARIANT_NAME K5_VARIANT_BOUND K5_VARIANT_NOCHECK
+for sg in 0 1100 0 1100; do
+  K5_ATTN_STAGGER=$sg timeout 300 python bench.py --steps 6 --warmup 3 --no-vae --no-configs --no-cpu-baseline > gpurun_out/tmp_bench.json 2>/dev/null
+  python - "$sg" <<PY | tee -a gpurun_out/r2_stagger_inloop.log
+import json,sys
+d=json.loads(open("gpurun_out/tmp_bench.json").read().strip().splitlines()[-1])
+print("stagger=%s ms/step %.1f  attention %.3f ms in-loop  frac %.4f  sm_mhz %s" % (sys.argv[1], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["clocks"]["sm_mhz"]))
+PY
+done
