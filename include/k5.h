@@ -205,6 +205,15 @@ int k5_attention_bounded(const void* Q, int ldq, const void* K, int ldk, const v
                          int Sk, int heads, float scale, const int32_t* kv_count, const int32_t* kv_index,
                          float score_bound_log2, void* stream);
 
+/* The same attention split over TWO launches by key rows - [0, split_row) first, whose unnormalised fp32 accumulators and
+ * row sums travel through `workspace` (float [Sq * heads * 68]), then [split_row, Sk) - the form the temporal shard uses to
+ * start on its local K | V slab while the foreign slabs are still arriving (csrc/engine.cu).  Partial sums are additive
+ * because the fixed-offset softmax has no row maximum: the result is BIT-IDENTICAL to k5_attention_bounded.  Needs a
+ * score bound in (0, 60]; split_row and Sk multiples of 128.  (Parity-test entry point.) */
+int k5_attention_bounded_split(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq,
+                               int Sk, int heads, float scale, float score_bound_log2, int split_row, float* workspace,
+                               void* stream);
+
 /* Debug builds of the library (-DK5_ATTN_TRACE) only: device buffer of 2*512*4 int64 clock stamps that CTA 0 of the
  * attention kernel fills (tools/attn_trace.py); K5_ERR_UNSUPPORTED otherwise. */
 int k5_debug_attn_trace(void* buf);

@@ -188,6 +188,40 @@ int k5_attention_bounded(const void* Q, int ldq, const void* K, int ldk, const v
                          static_cast<cudaStream_t>(stream), nullptr, score_bound_log2);
 }
 
+int k5_attention_bounded_split(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq,
+                               int Sk, int heads, float scale, float score_bound_log2, int split_row, float* workspace,
+                               void* stream) {
+    K5_NEED(Q);
+    K5_NEED(K);
+    K5_NEED(V);
+    K5_NEED(O);
+    K5_NEED(workspace);
+    if (split_row <= 0 || split_row >= Sk || split_row % 128 != 0 || Sk % 128 != 0) {
+        set_last_error("attention split: split_row and Sk must be multiples of 128 with 0 < split_row < Sk");
+        return K5_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AttnPartial part;
+    part.o = workspace;
+    part.l = workspace + static_cast<size_t>(Sq) * heads * 64;
+    part.mode = 1;
+    count_launch(2);
+    K5_TRY(attention_fwd(static_cast<const bf16*>(Q), ldq, static_cast<const bf16*>(K), ldk, static_cast<const bf16*>(V), ldv,
+                         static_cast<bf16*>(O), ldo, Sq, split_row, heads, scale, nullptr, nullptr, st, nullptr,
+                         score_bound_log2, nullptr, &part));
+    part.mode = 2;
+    AttnSlabs slabs;                 // two slabs, the first one already consumed: walk the second, no arrival flags
+    slabs.n = 2;
+    slabs.first = 0;
+    slabs.row0[0] = 0;
+    slabs.row0[1] = split_row;
+    slabs.row0[2] = Sk;
+    slabs.skip_own = true;
+    return attention_fwd(static_cast<const bf16*>(Q), ldq, static_cast<const bf16*>(K), ldk, static_cast<const bf16*>(V), ldv,
+                         static_cast<bf16*>(O), ldo, Sq, Sk - split_row, heads, scale, nullptr, nullptr, st, nullptr,
+                         score_bound_log2, &slabs, &part);
+}
+
 int k5_debug_attn_trace(void* buf) { return attention_debug_trace(static_cast<long long*>(buf)); }
 
 int k5_ln_rows(const void* x, int ldx, void* out, int ldo, int S, int D, const float* mul, const float* add, int plus_one,

@@ -288,6 +288,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         }
                     }
                     [[maybe_unused]] const int slab_own = slab;
+                    if constexpr (!SPARSE) {
+                        if (p.n_slabs > 0 && p.slab_skip_own) slab = slab + 1 == p.n_slabs ? 0 : slab + 1;   // own slab: done by the first launch
+                    }
                     for (int j = 0; j < nkv; ++j) {
                         int tile = SPARSE ? pairs[j] : j;
                         if constexpr (!SPARSE) {
@@ -495,7 +498,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < KT / 16; ++k)
-                            umma_ts(tO, tP + k * 8, vdesc0 + 128 * k, idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
+                            umma_ts(tO, tP + k * 8, vdesc0 + 128 * k, idesc_pv,
+                                    (j != 0 || k != 0 || (BOUNDED && !SPARSE && p.part_mode == 2)) ? 1u : 0u);
                         umma_commit(&B->pv_done[a]);
                         if constexpr (PAIR) umma_commit_mc(&B->v_empty[vst], 0x3);
                         else umma_commit(&B->v_empty[vst]);
@@ -549,8 +553,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint8_t* masks = SPARSE ? p.item_mask + static_cast<size_t>(item) * p.max_pairs : nullptr;
             const int qblk2 = (a * 2 + (wq >> 1)) * 2;     // bit position of this warp's 64-row query block
             int done = 0;                                  // KV tiles this query tile has taken part in (= j when dense)
+            [[maybe_unused]] float l4[4] = {0.f, 0.f, 0.f, 0.f};      // the four partial row sums (part_mode 1)
             if constexpr (BOUNDED && !W16) {
                 uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // row sum, carried over the item
+                if constexpr (!SPARSE) {
+                    if (p.part_mode == 2) {
+                        // continue where the launch over the local slab stopped: its fp32 accumulators go back into TMEM
+                        // (this thread read O of the previous item itself, so the columns are free), the row sums go on
+                        uint32_t o0[64];
+                        if (row < p.Sq) {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.part_o + (static_cast<size_t>(row) * p.heads + h) * HD);
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const uint4 v = __ldg(src + c);
+                                o0[4 * c] = v.x; o0[4 * c + 1] = v.y; o0[4 * c + 2] = v.z; o0[4 * c + 3] = v.w;
+                            }
+                            const float4 lp = __ldg(reinterpret_cast<const float4*>(p.part_l) + static_cast<size_t>(row) * p.heads + h);
+                            sum_a = pack_f32x2(lp.x, lp.y);
+                            sum_b = pack_f32x2(lp.z, lp.w);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 64; ++c) o0[c] = 0u;
+                        }
+                        tmem_st32(tO, o0);
+                        tmem_st32(tO + 32, o0 + 32);
+                        tmem_wait_st();
+                        tc_fence_before();
+                    }
+                }
                 for (int j = 0; j < nkv; ++j) {
                     bool actL = true, actR = true;
                     if constexpr (SPARSE) {
@@ -710,6 +740,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 float t0, t1;
                 unpack_f32x2(add_f32x2(sum_a, sum_b), t0, t1);
                 l = t0 + t1;
+                unpack_f32x2(sum_a, l4[0], l4[1]);
+                unpack_f32x2(sum_b, l4[2], l4[3]);
             } else if constexpr (BOUNDED) {
                 uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // half-row sum, carried over the item
                 const uint32_t tSh = tS + 64 * hf;                  // this thread's 64 score columns of every KV tile
@@ -1029,6 +1061,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int c = 0; c < 64; ++c) o[c] = 0u;
                 l = 0.f;
             }
+            if constexpr (BOUNDED && !W16 && !SPARSE) {
+                if (p.part_mode == 1) {
+                    if (row < p.Sq) {          // unnormalised fp32 partials for the launch over the remaining slabs
+                        uint4* dst = reinterpret_cast<uint4*>(p.part_o + (static_cast<size_t>(row) * p.heads + h) * HD);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) dst[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                        reinterpret_cast<float4*>(p.part_l)[static_cast<size_t>(row) * p.heads + h] = make_float4(l4[0], l4[1], l4[2], l4[3]);
+                    }
+                    continue;
+                }
+            }
             if (row < p.Sq) {
                 const float inv = l > 0.f ? 1.0f / l : 0.f;
                 uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.ldo + h * HD);
@@ -1182,7 +1225,7 @@ int configure_kernels() {
 
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st, AttnSparseWs* ws_in, float score_bound, const AttnSlabs* slabs) {
+                  cudaStream_t st, AttnSparseWs* ws_in, float score_bound, const AttnSlabs* slabs, const AttnPartial* part) {
     K5_REQUIRE(Sq > 0 && Sk > 0 && heads > 0, "attention: empty problem");
     const bool sparse = kv_count != nullptr;
     K5_REQUIRE((kv_count == nullptr) == (kv_index == nullptr), "attention: kv_count and kv_index go together");
@@ -1191,9 +1234,11 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     K5_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: pitches must be x8 elements");
     K5_REQUIRE((reinterpret_cast<uintptr_t>(O) & 15) == 0, "attention: output must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
+    // rows of the K | V matrices: with a slab schedule that leaves out the own slab, Sk counts the walked rows only
+    const int kv_rows = (slabs && slabs->n > 0) ? slabs->row0[slabs->n] : Sk;
     K5_TRY(make_tmap_2d_bf16(&tmQ, Q, Sq, static_cast<uint64_t>(heads) * HD, ldq, QT));
-    K5_TRY(make_tmap_2d_bf16(&tmK, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT));
-    K5_TRY(make_tmap_2d_bf16(&tmV, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT));
+    K5_TRY(make_tmap_2d_bf16(&tmK, K, kv_rows, static_cast<uint64_t>(heads) * HD, ldk, KT));
+    K5_TRY(make_tmap_2d_bf16(&tmV, V, kv_rows, static_cast<uint64_t>(heads) * HD, ldv, KT));
     static int npoly = -1, stagger = 0, split_tail = 1, use_bounded = 1;
     static std::mutex knob_mutex;
     static PerDevice<int> configured;
@@ -1231,6 +1276,10 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.max_pairs = 0;
     p.stagger = stagger;
     p.split_tail = split_tail;
+    p.part_o = nullptr;
+    p.part_l = nullptr;
+    p.part_mode = 0;
+    p.slab_skip_own = 0;
     p.slab_flags = nullptr;
     p.slab_err = nullptr;
     p.slab_timeout_ns = 0;
@@ -1240,9 +1289,10 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     for (int& t : p.slab_tile0) t = 0;
     if (slabs && slabs->n > 0) {     // flags == nullptr: the slab ORDER only (debug: single engine in a rank's order)
         K5_REQUIRE(!sparse, "attention: the overlapped gather is implemented for the dense kernel");
+        const int own_rows = slabs->skip_own && slabs->first >= 0 ? slabs->row0[slabs->first + 1] - slabs->row0[slabs->first] : 0;
         K5_REQUIRE(slabs->n >= 1 && slabs->n <= 8 && slabs->first >= -1 && slabs->first < slabs->n && Sk % KT == 0 &&
-                       (slabs->first >= 0 || slabs->flags == nullptr) &&
-                       slabs->row0[0] == 0 && slabs->row0[slabs->n] == Sk,
+                       (slabs->first >= 0 || slabs->flags == nullptr) && (!slabs->skip_own || (slabs->first >= 0 && slabs->n > 1)) &&
+                       slabs->row0[0] == 0 && slabs->row0[slabs->n] == Sk + own_rows,
                    "attention: bad slab schedule");
         for (int i = 0; i <= slabs->n; ++i) {
             K5_REQUIRE(slabs->row0[i] % KT == 0 && (i == 0 || slabs->row0[i] > slabs->row0[i - 1]),
@@ -1258,9 +1308,20 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         p.slab_epoch = slabs->epoch;
         p.n_slabs = slabs->n;
         p.slab_first = slabs->first;
+        p.slab_skip_own = slabs->skip_own ? 1 : 0;
     }
+    if (part && part->mode != 0) {
+        K5_REQUIRE(!sparse && (part->mode == 1 || part->mode == 2) && part->o && part->l &&
+                       (reinterpret_cast<uintptr_t>(part->o) & 15) == 0 && (reinterpret_cast<uintptr_t>(part->l) & 15) == 0,
+                   "attention: bad partial-sum buffers");
+        p.part_o = part->o;
+        p.part_l = part->l;
+        p.part_mode = part->mode;
+    }
+    K5_REQUIRE(!p.slab_skip_own || p.part_mode == 2, "attention: skipping the own slab needs the partials of the first launch");
     // fixed-offset softmax only under a proven bound that keeps exp2 and the fp32 row sums far from overflow
     const bool bounded = use_bounded && score_bound > 0.f && score_bound <= ATT_MAX_SCORE_BOUND;
+    K5_REQUIRE(p.part_mode == 0 || bounded, "attention: partial sums are additive only under the fixed-offset softmax (score bound)");
     const int n_qpairs = (Sq + 2 * QT - 1) / (2 * QT);
     const int n_items = n_qpairs * heads;
     const int grid = n_items < sm_count() ? n_items : sm_count();
@@ -1293,8 +1354,8 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         }
         if (bounded && npoly == 0 && pair_env && n_qpairs % 2 == 0 && grid % 2 == 0) {
             CUtensorMap tmK64, tmV64;
-            K5_TRY(make_tmap_2d_bf16(&tmK64, K, Sk, static_cast<uint64_t>(heads) * HD, ldk, KT / 2));
-            K5_TRY(make_tmap_2d_bf16(&tmV64, V, Sk, static_cast<uint64_t>(heads) * HD, ldv, KT / 2));
+            K5_TRY(make_tmap_2d_bf16(&tmK64, K, kv_rows, static_cast<uint64_t>(heads) * HD, ldk, KT / 2));
+            K5_TRY(make_tmap_2d_bf16(&tmV64, V, kv_rows, static_cast<uint64_t>(heads) * HD, ldv, KT / 2));
             cudaLaunchConfig_t cfg = {};
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;

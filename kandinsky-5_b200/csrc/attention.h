@@ -26,6 +26,13 @@ struct AttnParams {
     uint32_t slab_epoch;
     int n_slabs, slab_first;      // n_slabs == 0: natural tile order
     int slab_tile0[9];            // first 128-row KV tile of each slab; slab_tile0[n_slabs] = number of KV tiles
+    // Launch split by key slab (dense fixed-offset kernel; partial sums are additive because no row maximum exists):
+    // part_mode 1 writes the UNNORMALISED fp32 accumulators O [Sq, heads * 64] and the four fp32 partial row sums
+    // [Sq, heads, 4] instead of the bf16 output; part_mode 2 starts every row from those partials and normalises.
+    float* part_o;
+    float* part_l;
+    int part_mode;
+    int slab_skip_own;     // slab walk: leave out slab_first itself (it was consumed by the part_mode 1 launch)
     int stagger;           // cycles query tile 1 starts behind query tile 0 (keeps the two exp phases apart)
     int split_tail;        // split the items of a partial last round into their two query tiles (attention.cu)
 };
@@ -49,7 +56,14 @@ struct AttnSlabs {
     unsigned long long timeout_ns = 600ull * 1000000000ull;
     uint32_t epoch = 0;
     int n = 0, first = 0;         // first = -1 (debug, flags == nullptr): every query row starts at the slab holding it
-    int row0[9] = {};             // first row of each slab (multiples of 128); row0[n] = Sk
+    int row0[9] = {};             // first row of each slab (multiples of 128); row0[n] = rows of the K | V matrices
+    bool skip_own = false;        // walk the n - 1 foreign slabs only (Sk of the call = their rows); needs `part` mode 2
+};
+// Split of one attention over two launches (see AttnParams::part_mode); o: fp32 [Sq, heads * 64], l: fp32 [Sq, heads, 4]
+struct AttnPartial {
+    float* o = nullptr;
+    float* l = nullptr;
+    int mode = 0;                 // 1 = write partials (no bf16 output), 2 = continue from partials
 };
 
 // Q/K/V/O are row-major token matrices whose head h occupies columns [h*64, h*64+64).
@@ -58,7 +72,8 @@ struct AttnSlabs {
 // attention.cu); without one it keeps the running max with lazy rescaling.  Both compute the same softmax.
 int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo, int Sq,
                   int Sk, int heads, float softmax_scale, const int32_t* kv_count, const int32_t* kv_index,
-                  cudaStream_t st, AttnSparseWs* ws = nullptr, float score_bound = 0.f, const AttnSlabs* slabs = nullptr);
+                  cudaStream_t st, AttnSparseWs* ws = nullptr, float score_bound = 0.f, const AttnSlabs* slabs = nullptr,
+                  const AttnPartial* part = nullptr);
 
 // Debug builds (-DK5_ATTN_TRACE) only: device buffer [2][512][4] of clock64 stamps written by CTA 0 (attention.cu).
 int attention_debug_trace(long long* buf);

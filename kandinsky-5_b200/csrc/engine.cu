@@ -180,6 +180,9 @@ struct Engine {
         cudaEvent_t ev_copied[2][MAX_PEERS] = {};        // the pushes out of kv[buf] on copy stream i have read their source
         bool copied_valid[2] = {false, false};
         // time-out reporting of the cross-GPU waits (dist_barrier_kernel, the slab wait of the attention producer)
+        // overlapped all-gather: fp32 partials handed from the attention launch over the local slab to the one over the
+        // foreign slabs (attention.h: AttnPartial)
+        float *part_o = nullptr, *part_l = nullptr;
         uint32_t* err_host = nullptr;     // cudaHostAlloc(mapped): 0 = fine, else K5_DIST_ERR_*
         uint32_t* err_dev = nullptr;      // the same word as the device sees it
         unsigned long long timeout_ns = 600ull * 1000000000ull;
@@ -690,6 +693,8 @@ int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
     e->dist.overlap = cross;
     if (cross && !e->dist.ev_kv) {
         K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->dist.ev_kv, cudaEventDisableTiming));
+        K5_TRY(e->alloc(&e->dist.part_o, static_cast<size_t>(e->c.max_tokens) * e->D));
+        K5_TRY(e->alloc(&e->dist.part_l, static_cast<size_t>(e->c.max_tokens) * e->heads * 4));
         if (const char* ns = getenv("K5_DIST_COPY_STREAMS")) e->dist.n_copy_st = atoi(ns);
         e->dist.n_copy_st = e->dist.n_copy_st < 1 ? 1 : (e->dist.n_copy_st > MAX_PEERS - 1 ? MAX_PEERS - 1 : e->dist.n_copy_st);
         for (int i = 0; i < e->dist.n_copy_st; ++i) {
@@ -873,8 +878,30 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
     count_launch(1);
     const bool timed = e->timing && visual && e->ev_used + 2 <= e->ev.size();
     if (timed) K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used], st));
-    K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st, &e->sparse_ws,
-                         b.self.score_bound, slabs.n > 0 ? &slabs : nullptr));
+    const bool split = overlap && e->dist.world > 1 && b.self.score_bound > 0.f && b.self.score_bound <= 60.f &&
+                       !(getenv("K5_DIST_SPLIT") && atoi(getenv("K5_DIST_SPLIT")) == 0);
+    if (split) {
+        // The kernel runs heads outermost and every item sweeps ALL key tiles, so one launch over the whole K | V needs every
+        // foreign slab within its FIRST item (0.55 ms on 8 ranks) - the transfer (0.46 ms) would not hide.  Two launches:
+        // the local slab for all items first (its partial sums of O and l are additive under the fixed-offset softmax and
+        // travel as fp32), then the foreign slabs in arrival order.  The accumulation order per row is the same as in one
+        // launch that starts at the own slab, so the result is bit-identical to it (tests/gpu_shard_ranks.py).
+        AttnPartial part;
+        part.o = e->dist.part_o;
+        part.l = e->dist.part_l;
+        part.mode = 1;
+        const size_t own = static_cast<size_t>(e->tok0) * ldkv;
+        count_launch(1);
+        K5_TRY(attention_fwd(qkv, 3 * D, kp + own, ldkv, vp + own, ldkv, att, D, M, e->Sl, e->heads, 0.125f, nullptr, nullptr, st,
+                             &e->sparse_ws, b.self.score_bound, nullptr, &part));
+        part.mode = 2;
+        slabs.skip_own = true;
+        K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk - e->Sl, e->heads, 0.125f, nullptr, nullptr, st,
+                             &e->sparse_ws, b.self.score_bound, &slabs, &part));
+    } else {
+        K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st, &e->sparse_ws,
+                             b.self.score_bound, slabs.n > 0 ? &slabs : nullptr));
+    }
     if (timed) {
         K5_CHECK_CUDA(cudaEventRecord(e->ev[e->ev_used + 1], st));
         e->ev_used += 2;

@@ -55,6 +55,19 @@ def attention(q, k, v, heads, scale=None, kv_count=None, kv_index=None, out=None
     return out
 
 
+def attention_split(q, k, v, heads, score_bound, split_row, scale=None, out=None):
+    """k5_attention_bounded_split: the bounded attention over two launches by key rows (partials in fp32)."""
+    q, k, v = _bf16(q), _bf16(k), _bf16(v)
+    Sq, Sk = q.shape[0], k.shape[0]
+    if out is None:
+        out = torch.empty(Sq, heads * 64, device=q.device, dtype=torch.bfloat16)
+    ws = torch.empty(Sq * heads * 68, device=q.device, dtype=torch.float32)
+    check(lib().k5_attention_bounded_split(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out),
+                                           out.stride(0), Sq, Sk, heads, float(scale if scale is not None else 64 ** -0.5),
+                                           float(score_bound), int(split_row), ptr(ws), stream_ptr()))
+    return out
+
+
 def ln_rows(x, mul, add, plus_one=True, eps=1e-5, out=None):
     """bf16(LayerNorm(x) * (mul + plus_one) + add) row-wise."""
     x = _bf16(x)
