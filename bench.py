@@ -255,15 +255,25 @@ def cpu_arm(wl, budget_s):
     return v, m, cores, sample, "port"
 
 
-def bench_config(wl, world, nf, density):
+def default_dist_mode(world):
+    """The all-gather form engine_dist_init (csrc/engine.cu) picks for `world` ranks in separate processes."""
+    if world <= 1:
+        return 0
+    ov = os.environ.get("K5_DIST_OVERLAP", "")
+    return (2 if ov != "0" else 1) if ov != "" else (2 if world >= 8 else 1)
+
+
+def bench_config(wl, world, nf, density, dist_mode=1):
     """The `config` object of the JSON line - the same for the GPU arm and the `--impl reference` arm."""
     T = wl["T"]
     S = T * (wl["H"] // 2) * (wl["W"] // 2)
     fwd_per_step = 2 if abs(wl["w"] - 1.0) > 1e-6 else 1
     return {"workload": wl["name"], "tokens": S, "text_tokens": wl["L"], "forwards_per_step": fwd_per_step,
             "model": "Kandinsky-5 T2V Lite DiT 2.0B (random init, modulation re-randomised)",
-            "parallelism": (f"temporal shard x{world}: {nf} of {T} latent frames on rank 0, K|V all-gather fused into "
-                            "the QKV GEMM epilogue over NVLink peer memory") if world > 1 else "single GPU",
+            "parallelism": (f"temporal shard x{world}: {nf} of {T} latent frames on rank 0, " + (
+                "K|V all-gather overlapped with attention (copy-engine pushes over NVLink, per-slab arrival flags, local slab "
+                "attended first)" if dist_mode == 2 else
+                "K|V all-gather fused into the QKV GEMM epilogue over NVLink peer memory")) if world > 1 else "single GPU",
             "l2_policy": "per-step working set (>2 GB activations + 4 GB weights) exceeds the 126 MB L2",
             "nabla_density": density if wl["nabla"] else None}
 
@@ -298,8 +308,9 @@ def run_reference(args, wl):
     line = {
         "impl": "reference", "metric": "dit_latent_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": bench_config(wl, args.gpus, frame_partition(wl["T"], args.gpus)[0][1] if args.gpus > 1 else wl["T"], None),
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": bench_config(wl, args.gpus, frame_partition(wl["T"], args.gpus)[0][1] if args.gpus > 1 else wl["T"], None,
+                               default_dist_mode(args.gpus)),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -643,7 +654,7 @@ def run_k5(args, wl):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": bench_config(wl, world, nf, density),
+        "config": bench_config(wl, world, nf, density, model.dist_mode()),
         "ms_per_forward": ms_step / fwd_per_step,
         "model_tflops_per_forward": flops_fwd / 1e12,
         "model_tflops_achieved": flops_fwd * fwd_per_step / (ms_step * 1e-3) / 1e12,

@@ -33,6 +33,7 @@ int engine_dist_export(Engine* e, void* out);
 int engine_dist_init(Engine* e, int rank, int world, const void* handles);
 int engine_dist_barrier(Engine* e, cudaStream_t st);
 void engine_dist_info(Engine* e, int* f0, int* frames);
+int engine_dist_mode(Engine* e);
 int64_t launch_count(bool reset);
 void count_launch(int n);
 }  // namespace k5
@@ -135,6 +136,7 @@ int k5_dist_local_frames(k5_engine* e, int* first_frame, int* num_frames) {
     engine_dist_info(reinterpret_cast<Engine*>(e), first_frame, num_frames);
     return K5_OK;
 }
+int k5_dist_mode(k5_engine* e) { return e ? engine_dist_mode(reinterpret_cast<Engine*>(e)) : 0; }
 int64_t k5_launch_count(int reset) { return launch_count(reset != 0); }
 float k5_last_sparse_density(k5_engine* e) { return e ? engine_density(reinterpret_cast<Engine*>(e)) : 1.0f; }
 

@@ -684,12 +684,15 @@ int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
     bool cross = world > 1;
     for (int p = 0; p < world; ++p)
         if (p != rank && hs[p].pid == static_cast<int64_t>(getpid())) cross = false;
-    // Default: the all-gather fused into the QKV epilogue + one flag barrier.  The overlapped form (K5_DIST_OVERLAP=1) is
-    // bit-identical to a single engine walking the slabs in the owners' order and hides the transfer behind the attention,
-    // but measured no faster end to end on 2 and 8 GPUs (109.5 - 113 against 109.7 ms per step on 8):
-    // the time it takes out of the projection comes back as waiting inside the attention kernel.
+    // Two forms of the all-gather.  Scatter + barrier: the QKV epilogue stores the K | V columns into every rank's buffer,
+    // one flag barrier, then one attention launch over all of S.  Overlapped: copy engines push the slab, attention runs
+    // as two launches (local slab first, fp32 partials, then the foreign slabs as they arrive); bit-identical to a single
+    // engine walking the slabs in the owners' order.  Measured (ms per step at the 5 s size): 2 GPUs
+    // 375.4 scatter / 374.8 overlapped / 379.1 overlapped + split; 8 GPUs 111.0 scatter / 109.5 - 113 overlapped /
+    // 107.3 overlapped + split.  The transfer only outgrows the projection it hides in from 8 ranks on, so the overlapped
+    // form is the default there and scatter + barrier below; K5_DIST_OVERLAP=0 / 1 forces either.
     const char* ov = getenv("K5_DIST_OVERLAP");
-    cross = cross && ov != nullptr && atoi(ov) != 0;
+    cross = cross && (ov != nullptr ? atoi(ov) != 0 : world >= 8);
     e->dist.overlap = cross;
     if (cross && !e->dist.ev_kv) {
         K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->dist.ev_kv, cudaEventDisableTiming));
@@ -724,6 +727,8 @@ void engine_dist_info(Engine* e, int* f0, int* frames) {
     if (f0) *f0 = e->f0;
     if (frames) *frames = e->Tl;
 }
+
+int engine_dist_mode(Engine* e) { return !e->dist.on ? 0 : (e->dist.overlap ? 2 : 1); }
 
 namespace {
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "k5_dist_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "k5_dist_barrier": (c_int, [c_void_p, c_void_p]),
     "k5_dist_local_frames": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "k5_dist_mode": (c_int, [c_void_p]),
     "k5_vae_create": (c_int, [POINTER(K5VaeConfig), POINTER(c_void_p)]),
     "k5_vae_destroy": (None, [c_void_p]),
     "k5_vae_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64), c_int]),

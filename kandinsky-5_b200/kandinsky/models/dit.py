@@ -205,6 +205,10 @@ class DiffusionTransformer3D(nn.Module):
         check(lib().k5_dist_local_frames(self._engine, ctypes.byref(f0), ctypes.byref(n)))
         return f0.value, n.value
 
+    def dist_mode(self):
+        """0 = single GPU, 1 = K|V scatter from the QKV epilogue + flag barrier, 2 = overlapped all-gather (k5_dist_mode)."""
+        return int(lib().k5_dist_mode(self._engine)) if self._engine is not None else 0
+
     # ---- forward ---------------------------------------------------------------------------------------
     def set_grid(self, shape, visual_rope_pos, scale_factor, fractal):
         T, H, W = shape

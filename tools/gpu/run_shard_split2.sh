@@ -1,10 +1,8 @@
-# overlapped all-gather with the launch split by key slab: bit-identity, then bench for split / no split / scatter
-N=${1:-2}
+N=${1:-8}
 mkdir -p gpurun_out
 L=gpurun_out/r2_shard_split_${N}gpu.log
 : > $L
-[ -n "$SKIP_CHECK" ] || K5_SHARD_VERBOSE=1 K5_DIST_OVERLAP=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/gpu_shard_ranks.py 2>&1 | grep -E "shard x|Error|error|Traceback" >> $L
-for mode in "1 1" "1 0" "0 0"; do
+for mode in "1 1" "0 0"; do
   set -- $mode
   K5_DIST_OVERLAP=$1 K5_DIST_SPLIT=$2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 295$1$2 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_${N}gpu_split_$1$2.json 2>> gpurun_out/r2_bench_${N}gpu_split.err
   python - <<PY >> $L
