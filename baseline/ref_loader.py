@@ -51,9 +51,11 @@ def available():
 _mods = None
 
 
-def import_reference(cpu_attention=False):
+def import_reference(cpu_attention=False, keep_registered=False):
     """Returns {'utils','nn','dit','generation_utils'} modules of the reference.  cpu_attention: replace nn.FA by an
-    SDPA wrapper (flash_attn has no CPU kernels)."""
+    SDPA wrapper (flash_attn has no CPU kernels).  keep_registered: leave the reference's modules in sys.modules under
+    their own names (`kandinsky.models.nn` ...) - TorchDynamo re-imports a traced function's module by name, so the
+    compiled run needs it; the drop-in mirror of the same name cannot be imported in that process afterwards."""
     global _mods
     import torch
     import torch.nn.functional as F
@@ -79,10 +81,11 @@ def import_reference(cpu_attention=False):
                 mods[name.split(".")[-1]] = importlib.import_module(name)
         finally:
             # hand the name `kandinsky` back to whoever had it (the drop-in mirror lives under the same name)
-            for k in [k for k in sys.modules if k == "kandinsky" or k.startswith("kandinsky.")]:
-                del sys.modules[k]
-            for k, v in saved.items():
-                sys.modules[k] = v
+            if not keep_registered:
+                for k in [k for k in sys.modules if k == "kandinsky" or k.startswith("kandinsky.")]:
+                    del sys.modules[k]
+                for k, v in saved.items():
+                    sys.modules[k] = v
         _mods = mods
     if cpu_attention:
         def fa(q, k, v):       # flash_attn_func contract: [B,S,H,D] in / out, non-causal, scale d^-0.5

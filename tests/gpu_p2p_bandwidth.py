@@ -3,6 +3,8 @@
 temporal shard (csrc/engine.cu) can count on.  One process, all visible GPUs: GPU 0 pushes a slab-sized buffer (44 MB =
 6 144 rows x 3 584 bf16, the slab of an 8-rank shard at the 5 s size) to one peer on one stream, then to all peers at
 once on one stream per peer - the two forms the engine used (round 2: one stream, then one per peer).
+Then ALL GPUs push their slab to all peers at once (the real traffic pattern of a block: every rank r serves r-1, r-2, ...
+round-robin over a few copy streams), every copy queued behind one gate event so that host enqueue time stays outside.
 `nvidia-smi nvlink -gt d` reports N/A on these boxes, so timing the copies is the NVLink evidence there is."""
 import torch
 
@@ -55,6 +57,48 @@ def main():
         print(f"p2p 0 -> {n - 1} peers, ONE stream: {ms:.3f} ms for {(n - 1) * nbytes / 1e6:.0f} MB = {(n - 1) * nbytes / ms / 1e6:.0f} GB/s")
         ms = timed(all_parallel)
         print(f"p2p 0 -> {n - 1} peers, one stream PER PEER: {ms:.3f} ms for {(n - 1) * nbytes / 1e6:.0f} MB = {(n - 1) * nbytes / ms / 1e6:.0f} GB/s")
+    if n > 2:
+        all_to_all(n, nbytes)
+
+
+def all_to_all(n, nbytes):
+    """Every GPU pushes one slab to every peer, nearest consumer first, over `ns` copy streams per GPU; all copies wait
+    for one gate event, each GPU times its own pushes (gate passed -> last copy done); reported: the slowest GPU."""
+    src = [torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{r}") for r in range(n)]
+    dst = [[torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{p}") if p != r else None for p in range(n)] for r in range(n)]
+    for ns in (1, 2, 4, n - 1):
+        streams = [[torch.cuda.Stream(device=f"cuda:{r}") for _ in range(ns)] for r in range(n)]
+        worst = []
+        for rep in range(6):
+            torch.cuda.set_device(0)
+            gate = torch.cuda.Event()
+            torch.cuda._sleep(int(3e7))                      # ~15 ms: everything below is queued before the gate opens
+            gate.record()
+            t0, t1 = [], []
+            for r in range(n):
+                torch.cuda.set_device(r)
+                a = torch.cuda.Event(enable_timing=True)
+                for st in streams[r]:
+                    st.wait_event(gate)
+                a.record(streams[r][0])
+                for k in range(1, n):
+                    p = (r - k) % n
+                    with torch.cuda.stream(streams[r][(k - 1) % ns]):
+                        dst[r][p].copy_(src[r], non_blocking=True)
+                for st in streams[r][1:]:
+                    streams[r][0].wait_stream(st)
+                b = torch.cuda.Event(enable_timing=True)
+                b.record(streams[r][0])
+                t0.append(a)
+                t1.append(b)
+            for r in range(n):
+                torch.cuda.synchronize(r)
+            if rep >= 2:
+                worst.append(max(a.elapsed_time(b) for a, b in zip(t0, t1)))
+        ms = sum(worst) / len(worst)
+        print(f"p2p ALL {n} GPUs -> all peers at once, {ns} copy stream(s) per GPU: slowest GPU {ms:.3f} ms for "
+              f"{(n - 1) * nbytes / 1e6:.0f} MB out (and in) = {(n - 1) * nbytes / ms / 1e6:.0f} GB/s per GPU and direction")
+    torch.cuda.set_device(0)
 
 
 if __name__ == "__main__":
