@@ -139,7 +139,7 @@ int k5_dist_barrier(k5_engine* e, void* stream);
 int k5_dist_local_frames(k5_engine* e, int* first_frame, int* num_frames);
 /* Form of the K | V all-gather this engine uses for dense attention: 0 = not a shard, 1 = scatter from the QKV epilogue +
  * flag barrier, 2 = overlapped (copy-engine pushes, per-slab arrival flags, attention split into local / foreign
- * slabs).  Chosen in k5_dist_init: 2 from 8 ranks on, K5_DIST_OVERLAP=0|1 forces either (ranks in one process: 1). */
+ * slabs).  Chosen in k5_dist_init: 2 from 4 ranks on, K5_DIST_OVERLAP=0|1 forces either (ranks in one process: 1). */
 int k5_dist_mode(k5_engine* e);
 
 /* Number of kernels launched by this library since the counter was last reset (bench.py's gpu_launches). */
@@ -209,14 +209,15 @@ int k5_attention_bounded(const void* Q, int ldq, const void* K, int ldk, const v
                          int Sk, int heads, float scale, const int32_t* kv_count, const int32_t* kv_index,
                          float score_bound_log2, void* stream);
 
-/* The same attention split over TWO launches by key rows - [0, split_row) first, whose unnormalised fp32 accumulators and
- * row sums travel through `workspace` (float [Sq * heads * 68]), then [split_row, Sk) - the form the temporal shard uses to
- * start on its local K | V slab while the foreign slabs are still arriving (csrc/engine.cu).  Partial sums are additive
- * because the fixed-offset softmax has no row maximum: the result is BIT-IDENTICAL to k5_attention_bounded.  Needs a
- * score bound in (0, 60]; split_row and Sk multiples of 128.  (Parity-test entry point.) */
+/* The same attention split over TWO or THREE launches by key rows - [0, split_row) first, whose unnormalised fp32
+ * accumulators and row sums travel through `workspace` (float [Sq * heads * 68]), then [split_row, split_row2) (when
+ * split_row2 != 0: a middle launch that starts from the partials and leaves them again), then the rest - the form the
+ * temporal shard uses to start on its local K | V slab while the foreign slabs are still arriving (csrc/engine.cu).
+ * Partial sums are additive because the fixed-offset softmax has no row maximum: the result is BIT-IDENTICAL to
+ * k5_attention_bounded.  Needs a score bound in (0, 60]; the split rows and Sk multiples of 128.  (Parity-test entry point.) */
 int k5_attention_bounded_split(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq,
-                               int Sk, int heads, float scale, float score_bound_log2, int split_row, float* workspace,
-                               void* stream);
+                               int Sk, int heads, float scale, float score_bound_log2, int split_row, int split_row2,
+                               float* workspace, void* stream);
 
 /* Debug builds of the library (-DK5_ATTN_TRACE) only: device buffer of 2*512*4 int64 clock stamps that CTA 0 of the
  * attention kernel fills (tools/attn_trace.py); K5_ERR_UNSUPPORTED otherwise. */

@@ -191,37 +191,45 @@ int k5_attention_bounded(const void* Q, int ldq, const void* K, int ldk, const v
 }
 
 int k5_attention_bounded_split(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv, void* O, int ldo, int Sq,
-                               int Sk, int heads, float scale, float score_bound_log2, int split_row, float* workspace,
-                               void* stream) {
+                               int Sk, int heads, float scale, float score_bound_log2, int split_row, int split_row2,
+                               float* workspace, void* stream) {
     K5_NEED(Q);
     K5_NEED(K);
     K5_NEED(V);
     K5_NEED(O);
     K5_NEED(workspace);
-    if (split_row <= 0 || split_row >= Sk || split_row % 128 != 0 || Sk % 128 != 0) {
-        set_last_error("attention split: split_row and Sk must be multiples of 128 with 0 < split_row < Sk");
+    if (split_row <= 0 || split_row >= Sk || split_row % 128 != 0 || Sk % 128 != 0 ||
+        (split_row2 != 0 && (split_row2 <= split_row || split_row2 >= Sk || split_row2 % 128 != 0))) {
+        set_last_error("attention split: the split rows and Sk must be multiples of 128 with 0 < split_row < split_row2 < Sk");
         return K5_ERR_INVALID;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bf16 *q = static_cast<const bf16*>(Q), *k = static_cast<const bf16*>(K), *v = static_cast<const bf16*>(V);
     AttnPartial part;
     part.o = workspace;
     part.l = workspace + static_cast<size_t>(Sq) * heads * 64;
-    part.mode = 1;
-    count_launch(2);
-    K5_TRY(attention_fwd(static_cast<const bf16*>(Q), ldq, static_cast<const bf16*>(K), ldk, static_cast<const bf16*>(V), ldv,
-                         static_cast<bf16*>(O), ldo, Sq, split_row, heads, scale, nullptr, nullptr, st, nullptr,
-                         score_bound_log2, nullptr, &part));
-    part.mode = 2;
-    AttnSlabs slabs;                 // two slabs, the first one already consumed: walk the second, no arrival flags
-    slabs.n = 2;
+    part.mode = 1;                   // first slab: plain launch over rows [0, split_row) that leaves its partials
+    const int launches = split_row2 != 0 ? 3 : 2;
+    count_launch(launches);
+    K5_TRY(attention_fwd(q, ldq, k, ldk, v, ldv, static_cast<bf16*>(O), ldo, Sq, split_row, heads, scale, nullptr, nullptr, st,
+                         nullptr, score_bound_log2, nullptr, &part));
+    AttnSlabs slabs;                 // the slabs already consumed are skipped; no arrival flags
+    slabs.n = launches;
     slabs.first = 0;
     slabs.row0[0] = 0;
     slabs.row0[1] = split_row;
-    slabs.row0[2] = Sk;
-    slabs.skip_own = true;
-    return attention_fwd(static_cast<const bf16*>(Q), ldq, static_cast<const bf16*>(K), ldk, static_cast<const bf16*>(V), ldv,
-                         static_cast<bf16*>(O), ldo, Sq, Sk - split_row, heads, scale, nullptr, nullptr, st, nullptr,
-                         score_bound_log2, &slabs, &part);
+    slabs.row0[2] = split_row2 != 0 ? split_row2 : Sk;
+    slabs.row0[3] = Sk;
+    if (split_row2 != 0) {
+        part.mode = 3;               // middle launch: starts from the partials and leaves them again
+        slabs.skip = 1;
+        K5_TRY(attention_fwd(q, ldq, k, ldk, v, ldv, static_cast<bf16*>(O), ldo, Sq, split_row2 - split_row, heads, scale, nullptr,
+                             nullptr, st, nullptr, score_bound_log2, &slabs, &part));
+    }
+    part.mode = 2;
+    slabs.skip = launches - 1;
+    return attention_fwd(q, ldq, k, ldk, v, ldv, static_cast<bf16*>(O), ldo, Sq, Sk - slabs.row0[launches - 1], heads, scale,
+                         nullptr, nullptr, st, nullptr, score_bound_log2, &slabs, &part);
 }
 
 int k5_debug_attn_trace(void* buf) { return attention_debug_trace(static_cast<long long*>(buf)); }

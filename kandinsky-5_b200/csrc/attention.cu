@@ -289,7 +289,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                     [[maybe_unused]] const int slab_own = slab;
                     if constexpr (!SPARSE) {
-                        if (p.n_slabs > 0 && p.slab_skip_own) slab = slab + 1 == p.n_slabs ? 0 : slab + 1;   // own slab: done by the first launch
+                        if (p.n_slabs > 0)       // slabs of the rotated order that earlier launches of this attention consumed
+                            for (int sk = 0; sk < p.slab_skip; ++sk) slab = slab + 1 == p.n_slabs ? 0 : slab + 1;
                     }
                     for (int j = 0; j < nkv; ++j) {
                         int tile = SPARSE ? pairs[j] : j;
@@ -499,7 +500,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                         for (int k = 0; k < KT / 16; ++k)
                             umma_ts(tO, tP + k * 8, vdesc0 + 128 * k, idesc_pv,
-                                    (j != 0 || k != 0 || (BOUNDED && !SPARSE && p.part_mode == 2)) ? 1u : 0u);
+                                    (j != 0 || k != 0 || (BOUNDED && !SPARSE && (p.part_mode & 2))) ? 1u : 0u);
                         umma_commit(&B->pv_done[a]);
                         if constexpr (PAIR) umma_commit_mc(&B->v_empty[vst], 0x3);
                         else umma_commit(&B->v_empty[vst]);
@@ -557,18 +558,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if constexpr (BOUNDED && !W16) {
                 uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // row sum, carried over the item
                 if constexpr (!SPARSE) {
-                    if (p.part_mode == 2) {
-                        // continue where the launch over the local slab stopped: its fp32 accumulators go back into TMEM
+                    if (p.part_mode & 2) {
+                        // continue where the launch over the previous slabs stopped: its fp32 accumulators go back into TMEM
                         // (this thread read O of the previous item itself, so the columns are free), the row sums go on
                         uint32_t o0[64];
                         if (row < p.Sq) {
                             const uint4* src = reinterpret_cast<const uint4*>(p.part_o + (static_cast<size_t>(row) * p.heads + h) * HD);
 #pragma unroll
                             for (int c = 0; c < 16; ++c) {
-                                const uint4 v = __ldg(src + c);
+                                const uint4 v = src[c];          // (plain load: a middle launch writes these rows again at the end of the item)
                                 o0[4 * c] = v.x; o0[4 * c + 1] = v.y; o0[4 * c + 2] = v.z; o0[4 * c + 3] = v.w;
                             }
-                            const float4 lp = __ldg(reinterpret_cast<const float4*>(p.part_l) + static_cast<size_t>(row) * p.heads + h);
+                            const float4 lp = reinterpret_cast<const float4*>(p.part_l)[static_cast<size_t>(row) * p.heads + h];
                             sum_a = pack_f32x2(lp.x, lp.y);
                             sum_b = pack_f32x2(lp.z, lp.w);
                         } else {
@@ -1062,7 +1063,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 l = 0.f;
             }
             if constexpr (BOUNDED && !W16 && !SPARSE) {
-                if (p.part_mode == 1) {
+                if (p.part_mode & 1) {
                     if (row < p.Sq) {          // unnormalised fp32 partials for the launch over the remaining slabs
                         uint4* dst = reinterpret_cast<uint4*>(p.part_o + (static_cast<size_t>(row) * p.heads + h) * HD);
 #pragma unroll
@@ -1279,7 +1280,7 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     p.part_o = nullptr;
     p.part_l = nullptr;
     p.part_mode = 0;
-    p.slab_skip_own = 0;
+    p.slab_skip = 0;
     p.slab_flags = nullptr;
     p.slab_err = nullptr;
     p.slab_timeout_ns = 0;
@@ -1289,10 +1290,18 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
     for (int& t : p.slab_tile0) t = 0;
     if (slabs && slabs->n > 0) {     // flags == nullptr: the slab ORDER only (debug: single engine in a rank's order)
         K5_REQUIRE(!sparse, "attention: the overlapped gather is implemented for the dense kernel");
-        const int own_rows = slabs->skip_own && slabs->first >= 0 ? slabs->row0[slabs->first + 1] - slabs->row0[slabs->first] : 0;
+        // rows this launch walks: the slabs at positions [skip, skip + c) of the rotated order first, first + 1, ...
+        bool walk_ok = slabs->skip == 0 && slabs->row0[slabs->n] == Sk;
+        if (!walk_ok && slabs->first >= 0 && slabs->skip >= 0 && slabs->skip < slabs->n) {
+            int walked = 0;
+            for (int c = slabs->skip; c < slabs->n && !walk_ok; ++c) {
+                const int sl = (slabs->first + c) % slabs->n;
+                walked += slabs->row0[sl + 1] - slabs->row0[sl];
+                walk_ok = walked == Sk;
+            }
+        }
         K5_REQUIRE(slabs->n >= 1 && slabs->n <= 8 && slabs->first >= -1 && slabs->first < slabs->n && Sk % KT == 0 &&
-                       (slabs->first >= 0 || slabs->flags == nullptr) && (!slabs->skip_own || (slabs->first >= 0 && slabs->n > 1)) &&
-                       slabs->row0[0] == 0 && slabs->row0[slabs->n] == Sk + own_rows,
+                       (slabs->first >= 0 || slabs->flags == nullptr) && slabs->row0[0] == 0 && walk_ok,
                    "attention: bad slab schedule");
         for (int i = 0; i <= slabs->n; ++i) {
             K5_REQUIRE(slabs->row0[i] % KT == 0 && (i == 0 || slabs->row0[i] > slabs->row0[i - 1]),
@@ -1308,17 +1317,17 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
         p.slab_epoch = slabs->epoch;
         p.n_slabs = slabs->n;
         p.slab_first = slabs->first;
-        p.slab_skip_own = slabs->skip_own ? 1 : 0;
+        p.slab_skip = slabs->skip;
     }
     if (part && part->mode != 0) {
-        K5_REQUIRE(!sparse && (part->mode == 1 || part->mode == 2) && part->o && part->l &&
+        K5_REQUIRE(!sparse && part->mode >= 1 && part->mode <= 3 && part->o && part->l &&
                        (reinterpret_cast<uintptr_t>(part->o) & 15) == 0 && (reinterpret_cast<uintptr_t>(part->l) & 15) == 0,
                    "attention: bad partial-sum buffers");
         p.part_o = part->o;
         p.part_l = part->l;
         p.part_mode = part->mode;
     }
-    K5_REQUIRE(!p.slab_skip_own || p.part_mode == 2, "attention: skipping the own slab needs the partials of the first launch");
+    K5_REQUIRE(p.slab_skip == 0 || (p.part_mode & 2), "attention: skipping slabs needs the partials of the launches that consumed them");
     // fixed-offset softmax only under a proven bound that keeps exp2 and the fp32 row sums far from overflow
     const bool bounded = use_bounded && score_bound > 0.f && score_bound <= ATT_MAX_SCORE_BOUND;
     K5_REQUIRE(p.part_mode == 0 || bounded, "attention: partial sums are additive only under the fixed-offset softmax (score bound)");

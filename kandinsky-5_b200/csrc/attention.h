@@ -27,12 +27,13 @@ struct AttnParams {
     int n_slabs, slab_first;      // n_slabs == 0: natural tile order
     int slab_tile0[9];            // first 128-row KV tile of each slab; slab_tile0[n_slabs] = number of KV tiles
     // Launch split by key slab (dense fixed-offset kernel; partial sums are additive because no row maximum exists):
-    // part_mode 1 writes the UNNORMALISED fp32 accumulators O [Sq, heads * 64] and the four fp32 partial row sums
-    // [Sq, heads, 4] instead of the bf16 output; part_mode 2 starts every row from those partials and normalises.
+    // part_mode bit 0: the launch ends by writing the UNNORMALISED fp32 accumulators O [Sq, heads * 64] and the four fp32
+    // partial row sums [Sq, heads, 4] instead of the bf16 output; bit 1: every row starts from those partials (1 = first
+    // launch, 3 = a middle launch, 2 = the last launch, which normalises).
     float* part_o;
     float* part_l;
     int part_mode;
-    int slab_skip_own;     // slab walk: leave out slab_first itself (it was consumed by the part_mode 1 launch)
+    int slab_skip;         // slab walk: leave out the first slab_skip slabs of the rotated order (earlier launches consumed them)
     int stagger;           // cycles query tile 1 starts behind query tile 0 (keeps the two exp phases apart)
     int split_tail;        // split the items of a partial last round into their two query tiles (attention.cu)
 };
@@ -57,13 +58,14 @@ struct AttnSlabs {
     uint32_t epoch = 0;
     int n = 0, first = 0;         // first = -1 (debug, flags == nullptr): every query row starts at the slab holding it
     int row0[9] = {};             // first row of each slab (multiples of 128); row0[n] = rows of the K | V matrices
-    bool skip_own = false;        // walk the n - 1 foreign slabs only (Sk of the call = their rows); needs `part` mode 2
+    int skip = 0;                 // leave out the first `skip` slabs of the order first, first + 1, ... (consumed by earlier launches
+                                  // of the same attention; needs `part` mode 2 or 3); Sk of the call = the rows of the slabs walked
 };
 // Split of one attention over two launches (see AttnParams::part_mode); o: fp32 [Sq, heads * 64], l: fp32 [Sq, heads, 4]
 struct AttnPartial {
     float* o = nullptr;
     float* l = nullptr;
-    int mode = 0;                 // 1 = write partials (no bf16 output), 2 = continue from partials
+    int mode = 0;                 // bit 0: write partials (no bf16 output); bit 1: start from partials; 3 = a middle launch
 };
 
 // Q/K/V/O are row-major token matrices whose head h occupies columns [h*64, h*64+64).

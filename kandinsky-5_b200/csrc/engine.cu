@@ -689,10 +689,11 @@ int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
     // as two launches (local slab first, fp32 partials, then the foreign slabs as they arrive); bit-identical to a single
     // engine walking the slabs in the owners' order.  Measured (ms per step at the 5 s size): 2 GPUs
     // 375.4 scatter / 374.8 overlapped / 379.1 overlapped + split; 8 GPUs 111.0 scatter / 109.5 - 113 overlapped /
-    // 107.3 overlapped + split.  The transfer only outgrows the projection it hides in from 8 ranks on, so the overlapped
-    // form is the default there and scatter + barrier below; K5_DIST_OVERLAP=0 / 1 forces either.
+    // 107.3 overlapped + split; 4 GPUs 198.8 scatter / 196.1 overlapped + split.  On 2 ranks the transfer hides inside the
+    // projection that produces it, from 4 ranks on it outgrows it, so the overlapped form is the default from 4 ranks on
+    // and scatter + barrier below; K5_DIST_OVERLAP=0 / 1 forces either.
     const char* ov = getenv("K5_DIST_OVERLAP");
-    cross = cross && (ov != nullptr ? atoi(ov) != 0 : world >= 8);
+    cross = cross && (ov != nullptr ? atoi(ov) != 0 : world >= 4);
     e->dist.overlap = cross;
     if (cross && !e->dist.ev_kv) {
         K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->dist.ev_kv, cudaEventDisableTiming));
@@ -887,21 +888,44 @@ int self_attention(Engine* e, const Block& b, bf16* x, bf16* xn, bf16* qkv, bf16
                        !(getenv("K5_DIST_SPLIT") && atoi(getenv("K5_DIST_SPLIT")) == 0);
     if (split) {
         // The kernel runs heads outermost and every item sweeps ALL key tiles, so one launch over the whole K | V needs every
-        // foreign slab within its FIRST item (0.55 ms on 8 ranks) - the transfer (0.46 ms) would not hide.  Two launches:
+        // foreign slab within its FIRST item (0.55 ms on 8 ranks) - the transfer would not hide.  Two launches instead:
         // the local slab for all items first (its partial sums of O and l are additive under the fixed-offset softmax and
-        // travel as fp32), then the foreign slabs in arrival order.  The accumulation order per row is the same as in one
-        // launch that starts at the own slab, so the result is bit-identical to it (tests/gpu_shard_ranks.py).
+        // travel as fp32), then the foreign slabs in arrival order.  The accumulation order per row is that of one launch
+        // starting at the own slab, so the result is bit-identical to it (tests/gpu_shard_ranks.py).
+        // K5_DIST_SPLIT_GROUPS=2 walks the foreign slabs in TWO launches (the nearest (W - 1) / 2 first, a middle launch that
+        // reads and writes the partials): with all ranks pushing at once a copy engine delivers ~370 GB/s
+        // (tests/gpu_p2p_bandwidth.py), one 44 MB slab per 0.12 ms on 8 ranks, while an item consumes one per 0.06 ms, so the
+        // last launch would start with its slabs landed.  Bit-identical on 8 GPUs as well, but measured no faster (108.7
+        // against 107.3 ms per step, profiles/r2_shard_final_8gpu.log): late slabs are not what the split form still loses.
         AttnPartial part;
         part.o = e->dist.part_o;
         part.l = e->dist.part_l;
         part.mode = 1;
         const size_t own = static_cast<size_t>(e->tok0) * ldkv;
-        count_launch(1);
+        const int W_ = e->dist.world, r = e->dist.rank;
+        int groups = 1;
+        if (const char* gs = getenv("K5_DIST_SPLIT_GROUPS")) groups = atoi(gs) >= 2 && W_ >= 3 ? 2 : 1;
+        count_launch(groups);
         K5_TRY(attention_fwd(qkv, 3 * D, kp + own, ldkv, vp + own, ldkv, att, D, M, e->Sl, e->heads, 0.125f, nullptr, nullptr, st,
                              &e->sparse_ws, b.self.score_bound, nullptr, &part));
+        const int near = groups == 2 ? (W_ - 1) / 2 : W_ - 1;     // foreign slabs of the first foreign launch
+        int rows_near = 0;
+        for (int c = 1; c <= near; ++c) {
+            const int sl = (r + c) % W_;
+            rows_near += slabs.row0[sl + 1] - slabs.row0[sl];
+        }
+        if (groups == 2) {
+            part.mode = 3;
+            slabs.skip = 1;
+            K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, rows_near, e->heads, 0.125f, nullptr, nullptr, st,
+                                 &e->sparse_ws, b.self.score_bound, &slabs, &part));
+            slabs.skip = 1 + near;
+            rows_near = Sk - e->Sl - rows_near;
+        } else {
+            slabs.skip = 1;
+        }
         part.mode = 2;
-        slabs.skip_own = true;
-        K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk - e->Sl, e->heads, 0.125f, nullptr, nullptr, st,
+        K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, rows_near, e->heads, 0.125f, nullptr, nullptr, st,
                              &e->sparse_ws, b.self.score_bound, &slabs, &part));
     } else {
         K5_TRY(attention_fwd(qkv, 3 * D, kp, ldkv, vp, ldkv, att, D, M, Sk, e->heads, 0.125f, cnt, idx, st, &e->sparse_ws,

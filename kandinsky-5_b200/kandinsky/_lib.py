@@ -72,7 +72,7 @@ SIGNATURES = {
     "k5_attention_bounded": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                      c_int, c_float, c_void_p, c_void_p, c_float, c_void_p]),
     "k5_attention_bounded_split": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
-                                           c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
+                                           c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),
     "k5_debug_attn_trace": (c_int, [c_void_p]),
     "k5_ln_rows": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     "k5_nabla_select": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,

@@ -55,8 +55,8 @@ def attention(q, k, v, heads, scale=None, kv_count=None, kv_index=None, out=None
     return out
 
 
-def attention_split(q, k, v, heads, score_bound, split_row, scale=None, out=None):
-    """k5_attention_bounded_split: the bounded attention over two launches by key rows (partials in fp32)."""
+def attention_split(q, k, v, heads, score_bound, split_row, scale=None, out=None, split_row2=0):
+    """k5_attention_bounded_split: the bounded attention over two (three with split_row2) launches by key rows (partials in fp32)."""
     q, k, v = _bf16(q), _bf16(k), _bf16(v)
     Sq, Sk = q.shape[0], k.shape[0]
     if out is None:
@@ -64,7 +64,7 @@ def attention_split(q, k, v, heads, score_bound, split_row, scale=None, out=None
     ws = torch.empty(Sq * heads * 68, device=q.device, dtype=torch.float32)
     check(lib().k5_attention_bounded_split(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out),
                                            out.stride(0), Sq, Sk, heads, float(scale if scale is not None else 64 ** -0.5),
-                                           float(score_bound), int(split_row), ptr(ws), stream_ptr()))
+                                           float(score_bound), int(split_row), int(split_row2), ptr(ws), stream_ptr()))
     return out
 
 

@@ -183,20 +183,25 @@ def test_attention_bounded_matches_torch_and_general_kernel(Sq, Sk, heads, wq, w
     assert rel_l2(out, gen) < 6e-3
 
 
-@pytest.mark.parametrize("Sq,Sk,split,heads", [(512, 512, 128, 2), (768, 1920, 1152, 4), (300, 1024, 512, 3), (6144, 12288, 1536, 28)])
-def test_attention_split_by_key_rows_is_bit_identical(Sq, Sk, split, heads):
+@pytest.mark.parametrize("Sq,Sk,split,split2,heads", [(512, 512, 128, 0, 2), (768, 1920, 1152, 0, 4), (300, 1024, 512, 0, 3),
+                                                       (6144, 12288, 1536, 0, 28), (512, 768, 256, 384, 2), (300, 1920, 128, 1152, 3),
+                                                       (6144, 12288, 1536, 6144, 28)])
+def test_attention_split_by_key_rows_is_bit_identical(Sq, Sk, split, split2, heads):
     """k5_attention_bounded_split: key rows [0, split) in one launch (unnormalised fp32 partials of O and the row sums),
-    the rest in a second launch that starts from them - what a shard rank does to start on its local K | V slab while the
-    foreign slabs arrive.  No row maximum exists under a score bound, so the partials are additive and the two launches
-    must reproduce the single launch BIT FOR BIT (same accumulation order per row)."""
+    the rest in a second launch that starts from them (with split2: a middle launch over [split, split2) that starts from
+    the partials AND leaves them again) - what a shard rank does to start on its local K | V slab while the foreign slabs
+    arrive.  No row maximum exists under a score bound, so the partials are additive and the launches must reproduce
+    the single launch BIT FOR BIT (same accumulation order per row)."""
     q, k = _rms_heads(_rand((Sq, heads * 64), 40)), _rms_heads(_rand((Sk, heads * 64), 41))
     v = _rand((Sk, heads * 64), 42)
     one = _ops().attention(q, k, v, heads, score_bound=_bound())
-    two = _ops().attention_split(q, k, v, heads, _bound(), split)
+    two = _ops().attention_split(q, k, v, heads, _bound(), split, split_row2=split2)
     assert torch.equal(one, two)
     assert rel_l2(two, _attn_ref(q, k, v, heads)) < 8e-3
     with pytest.raises(ValueError):
         _ops().attention_split(q, k, v, heads, _bound(), split + 64)
+    with pytest.raises(ValueError):
+        _ops().attention_split(q, k, v, heads, _bound(), split, split_row2=split)
 
 
 def test_attention_bound_above_limit_selects_general_kernel():
