@@ -183,7 +183,11 @@ __device__ __forceinline__ void exp2_poly2_nc(float x0, float x1, float& p0, flo
 // (148 CTAs x 12 MB of K|V per head otherwise).  A ring stage is handed back when the issuers of BOTH CTAs are done with
 // it (their commits arrive on both CTAs' barriers).  Everything else - Q, TMEM, the softmax warps - is per CTA as before.
 // The kernel sits at the 1 kW power cap, so what the fabric does not burn comes back as clock.
-template <bool SPARSE, int NPOLY, bool BOUNDED, bool W16 = false, bool PAIR = false>
+// PART (dense BOUNDED only): the launch is one of several over key slabs of the same attention (AttnParams::part_mode,
+// slab_skip).  A template parameter, not a run-time branch: the instantiation without it is the code ptxas scheduled before
+// the split existed - run-time branches around the exponential stream changed its interleaving (SASS of the hot loop 25 %
+// similar) and cost 3 % in the single-GPU step (19.17 against 18.45 - 18.7 ms per launch).
+template <bool SPARSE, int NPOLY, bool BOUNDED, bool W16 = false, bool PAIR = false, bool PART = false>
 __global__ void __launch_bounds__(W16 ? ATT_THREADS_B : ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -197,6 +201,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // softmax warps 0 .. NSW-1, then producer, issuer of query tile 0, TMEM allocator, issuer of query tile 1
     static_assert(!W16 || BOUNDED, "two threads per row need the fixed-offset softmax");
     static_assert(!PAIR || !SPARSE, "CTA pairs share dense K / V streams only");
+    static_assert(!PART || (BOUNDED && !W16 && !SPARSE), "launches split by key slab need the dense fixed-offset kernel");
     [[maybe_unused]] const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     constexpr int NSW = W16 ? 16 : 8;
     constexpr int W_PROD = NSW, W_ISS0 = NSW + 1, W_ALLOC = NSW + 2, W_ISS1 = NSW + 3;
@@ -289,8 +294,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     }
                     [[maybe_unused]] const int slab_own = slab;
                     if constexpr (!SPARSE) {
-                        if (p.n_slabs > 0)       // slabs of the rotated order that earlier launches of this attention consumed
-                            for (int sk = 0; sk < p.slab_skip; ++sk) slab = slab + 1 == p.n_slabs ? 0 : slab + 1;
+                        if constexpr (PART) {
+                            if (p.n_slabs > 0)   // slabs of the rotated order that earlier launches of this attention consumed
+                                for (int sk = 0; sk < p.slab_skip; ++sk) slab = slab + 1 == p.n_slabs ? 0 : slab + 1;
+                        }
                     }
                     for (int j = 0; j < nkv; ++j) {
                         int tile = SPARSE ? pairs[j] : j;
@@ -500,7 +507,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                         for (int k = 0; k < KT / 16; ++k)
                             umma_ts(tO, tP + k * 8, vdesc0 + 128 * k, idesc_pv,
-                                    (j != 0 || k != 0 || (BOUNDED && !SPARSE && (p.part_mode & 2))) ? 1u : 0u);
+                                    (j != 0 || k != 0 || (PART && (p.part_mode & 2))) ? 1u : 0u);
                         umma_commit(&B->pv_done[a]);
                         if constexpr (PAIR) umma_commit_mc(&B->v_empty[vst], 0x3);
                         else umma_commit(&B->v_empty[vst]);
@@ -557,7 +564,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             [[maybe_unused]] float l4[4] = {0.f, 0.f, 0.f, 0.f};      // the four partial row sums (part_mode 1)
             if constexpr (BOUNDED && !W16) {
                 uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // row sum, carried over the item
-                if constexpr (!SPARSE) {
+                if constexpr (PART) {
                     if (p.part_mode & 2) {
                         // continue where the launch over the previous slabs stopped: its fp32 accumulators go back into TMEM
                         // (this thread read O of the previous item itself, so the columns are free), the row sums go on
@@ -741,8 +748,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 float t0, t1;
                 unpack_f32x2(add_f32x2(sum_a, sum_b), t0, t1);
                 l = t0 + t1;
-                unpack_f32x2(sum_a, l4[0], l4[1]);
-                unpack_f32x2(sum_b, l4[2], l4[3]);
+                if constexpr (PART) {
+                    unpack_f32x2(sum_a, l4[0], l4[1]);
+                    unpack_f32x2(sum_b, l4[2], l4[3]);
+                }
             } else if constexpr (BOUNDED) {
                 uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = pack_f32x2(0.f, 0.f);   // half-row sum, carried over the item
                 const uint32_t tSh = tS + 64 * hf;                  // this thread's 64 score columns of every KV tile
@@ -1062,7 +1071,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int c = 0; c < 64; ++c) o[c] = 0u;
                 l = 0.f;
             }
-            if constexpr (BOUNDED && !W16 && !SPARSE) {
+            if constexpr (PART) {
                 if (p.part_mode & 1) {
                     if (row < p.Sq) {          // unnormalised fp32 partials for the launch over the remaining slabs
                         uint4* dst = reinterpret_cast<uint4*>(p.part_o + (static_cast<size_t>(row) * p.heads + h) * HD);
@@ -1215,6 +1224,10 @@ int configure_set() {
 int configure_kernels() {
     K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false, 0, true, false, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false, 0, true, false, true, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    K5_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false, 0, true, false, false, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     K5_TRY((configure_set<false, false>()));
     K5_TRY((configure_set<true, false>()));
     K5_TRY((configure_set<false, true>()));
@@ -1361,6 +1374,8 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
             const char* ev = getenv("K5_ATTN_PAIR");
             pair_env = ev ? (atoi(ev) != 0) : ATT_PAIR_DEFAULT;
         }
+        const bool parted = p.part_mode != 0 || p.slab_skip != 0;      // one of several launches over key slabs (PART kernels)
+        K5_REQUIRE(!parted || npoly == 0, "attention: launches split by key slab exist for K5_ATTN_POLY=0 only");
         if (bounded && npoly == 0 && pair_env && n_qpairs % 2 == 0 && grid % 2 == 0) {
             CUtensorMap tmK64, tmV64;
             K5_TRY(make_tmap_2d_bf16(&tmK64, K, kv_rows, static_cast<uint64_t>(heads) * HD, ldk, KT / 2));
@@ -1392,7 +1407,10 @@ int attention_fwd(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V,
                 resident = 2 * max_pairs.v[dev];
             }
             cfg.gridDim = dim3(static_cast<unsigned>(grid < resident ? grid : resident));
-            K5_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attention_fwd_kernel<false, 0, true, false, true>, tmQ, tmK64, tmV64, p));
+            if (parted) K5_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attention_fwd_kernel<false, 0, true, false, true, true>, tmQ, tmK64, tmV64, p));
+            else K5_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attention_fwd_kernel<false, 0, true, false, true>, tmQ, tmK64, tmV64, p));
+        } else if (bounded && parted) {
+            attention_fwd_kernel<false, 0, true, false, false, true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
         } else if (bounded) {
             launch_kernel<false, true>(npoly, grid, tmQ, tmK, tmV, p, st);
         } else {
