@@ -39,6 +39,32 @@ def test_library_is_sm100a_and_uses_tcgen05_tma():
     assert "HMMA.16816" not in sass                               # no legacy mma.sync path
 
 
+def test_dense_attention_hot_loop_is_the_tuned_schedule():
+    """The exponential stream of the dense attention kernel was tuned against ptxas's interleaving; an edit elsewhere in the
+    kernel can change it silently (round 2: -3 % in the step from two run-time branches outside the loop).  The opcode
+    sequence of that region must match the fingerprint taken from the build that was measured and profiled
+    (profiles/attention_hotloop_fingerprint.json, tools/sass_fingerprint.py); after a DELIBERATE change re-measure on the
+    GPU and refresh it with `python tools/sass_fingerprint.py kandinsky-5_b200/libk5.so --update`."""
+    import json
+    import shutil
+    import sys
+
+    from kandinsky import _lib
+
+    if not shutil.which("cuobjdump") or not shutil.which("nvcc"):
+        pytest.skip("CUDA toolkit binaries not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_fingerprint as fp
+
+    want = json.load(open(fp.JSON))
+    if fp.nvcc_version() != want["nvcc"]:
+        pytest.skip(f"fingerprint was taken with nvcc {want['nvcc']}")
+    _lib.lib()
+    got = fp.fingerprint(_lib.LIB_PATH, want["kernel"])
+    assert got["hot_loop_mix"] == want["hot_loop_mix"]
+    assert got["hot_loop_sha1"] == want["hot_loop_sha1"], "ptxas scheduled the dense softmax loop differently: re-measure"
+
+
 def test_version_and_error_channel_without_gpu():
     from kandinsky import _lib
 
