@@ -260,7 +260,7 @@ def default_dist_mode(world):
     if world <= 1:
         return 0
     ov = os.environ.get("K5_DIST_OVERLAP", "")
-    return (2 if ov != "0" else 1) if ov != "" else (2 if world >= 4 else 1)
+    return (2 if ov != "0" else 1) if ov != "" else (2 if world >= 8 else 1)
 
 
 def bench_config(wl, world, nf, density, dist_mode=1):

@@ -139,7 +139,7 @@ int k5_dist_barrier(k5_engine* e, void* stream);
 int k5_dist_local_frames(k5_engine* e, int* first_frame, int* num_frames);
 /* Form of the K | V all-gather this engine uses for dense attention: 0 = not a shard, 1 = scatter from the QKV epilogue +
  * flag barrier, 2 = overlapped (copy-engine pushes, per-slab arrival flags, attention split into local / foreign
- * slabs).  Chosen in k5_dist_init: 2 from 4 ranks on, K5_DIST_OVERLAP=0|1 forces either (ranks in one process: 1). */
+ * slabs).  Chosen in k5_dist_init: 2 from 8 ranks on, K5_DIST_OVERLAP=0|1 forces either (ranks in one process: 1). */
 int k5_dist_mode(k5_engine* e);
 
 /* Number of kernels launched by this library since the counter was last reset (bench.py's gpu_launches). */

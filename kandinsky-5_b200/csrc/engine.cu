@@ -689,11 +689,13 @@ int engine_dist_init(Engine* e, int rank, int world, const void* handles) {
     // as two launches (local slab first, fp32 partials, then the foreign slabs as they arrive); bit-identical to a single
     // engine walking the slabs in the owners' order.  Measured (ms per step at the 5 s size): 2 GPUs
     // 375.4 scatter / 374.8 overlapped / 379.1 overlapped + split; 8 GPUs 111.0 scatter / 109.5 - 113 overlapped /
-    // 107.3 overlapped + split; 4 GPUs 198.8 scatter / 196.1 overlapped + split.  On 2 ranks the transfer hides inside the
-    // projection that produces it, from 4 ranks on it outgrows it, so the overlapped form is the default from 4 ranks on
-    // and scatter + barrier below; K5_DIST_OVERLAP=0 / 1 forces either.
+    // 107.3 overlapped + split; 4 GPUs 198.8 scatter / 196.1 overlapped + split - all with the attention loop of that day,
+    // which was 2.6 % slower than the tuned one in BOTH forms (profiles/r2_attention_part_template.md).  Since then the plain
+    // dense kernel (scatter form) has the tuned loop back while the split launches (PART kernels) keep the slower one, which
+    // moves the scatter numbers to ~194.8 (4 GPUs) and ~109.0 (8 GPUs): the overlapped form is the default from 8 ranks on,
+    // scatter + barrier below; K5_DIST_OVERLAP=0 / 1 forces either.
     const char* ov = getenv("K5_DIST_OVERLAP");
-    cross = cross && (ov != nullptr ? atoi(ov) != 0 : world >= 4);
+    cross = cross && (ov != nullptr ? atoi(ov) != 0 : world >= 8);
     e->dist.overlap = cross;
     if (cross && !e->dist.ev_kv) {
         K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->dist.ev_kv, cudaEventDisableTiming));

@@ -47,7 +47,7 @@ def main():
     npooled = torch.randn(1, 768, generator=g).to(torch.bfloat16).to(dev)
     pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
     ov = os.environ.get("K5_DIST_OVERLAP", "")
-    overlapped = ov not in ("", "0") if ov != "" else world >= 4       # the engine's default (csrc/engine.cu, engine_dist_init)
+    overlapped = ov not in ("", "0") if ov != "" else world >= 8       # the engine's default (csrc/engine.cu, engine_dist_init)
     ref_nat = None
     if overlapped:
         ref_nat = full(img, text, pooled, 700.0, pos, torch.arange(L), scale_factor=(1.0, 2.0, 2.0)).clone()
