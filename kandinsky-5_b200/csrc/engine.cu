@@ -128,6 +128,8 @@ struct Engine {
     float *tfeat = nullptr, *t1 = nullptr, *tembed = nullptr, *modOut = nullptr;
     float2 *rope_v = nullptr, *rope_t = nullptr, *rope_t_arange = nullptr;
     int *pos_dev = nullptr;         // [T + Hp + Wp] then text positions at +4096
+    int *pos_pinned = nullptr;      // pinned staging of caller-given text positions (lazily allocated, 4096 ints)
+    cudaEvent_t pos_ev = nullptr;   // recorded behind the copy that reads pos_pinned
     bf16 *v_c = nullptr, *v_u = nullptr;
     // MagCache (magcache_utils.py): the embedded input of the visual stack and one cached block-stack residual per
     // CFG branch; allocated on first use
@@ -215,6 +217,8 @@ struct Engine {
     }
     ~Engine() {
         if (dist.err_host) cudaFreeHost(dist.err_host);
+        if (pos_pinned) cudaFreeHost(pos_pinned);
+        if (pos_ev) cudaEventDestroy(pos_ev);
         for (cudaStream_t cs : dist.copy_st)
             if (cs) cudaStreamDestroy(cs);
         if (dist.ev_kv) cudaEventDestroy(dist.ev_kv);
@@ -1050,10 +1054,20 @@ int engine_forward(Engine* e, const float* x, int Cx, const bf16* text, int L, c
     // text RoPE (nn.py:110-116): arange positions use the table built at finalize (a prefix of it)
     const float2* rope_t = e->rope_t_arange;
     if (text_pos) {
-        std::vector<int> pos(text_pos, text_pos + L);
-        for (int v : pos) K5_REQUIRE(v >= 0 && v < 1024, "forward: text RoPE position out of range [0,1024)");
-        K5_CHECK_CUDA(cudaMemcpyAsync(e->pos_dev + 4096, pos.data(), L * sizeof(int), cudaMemcpyHostToDevice, st));
-        K5_CHECK_CUDA(cudaStreamSynchronize(st));   // pos is a local staging buffer
+        K5_REQUIRE(L <= 4096, "forward: more than 4096 text positions");
+        for (int i = 0; i < L; ++i)
+            K5_REQUIRE(text_pos[i] >= 0 && text_pos[i] < 1024, "forward: text RoPE position out of range [0,1024)");
+        // Pinned staging owned by the engine: the copy is asynchronous and the stream is NOT drained (a pageable source
+        // would make cudaMemcpyAsync synchronise it).  The only wait is for the previous forward's copy of this buffer.
+        if (!e->pos_pinned) {
+            K5_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->pos_pinned), 4096 * sizeof(int), cudaHostAllocDefault));
+            K5_CHECK_CUDA(cudaEventCreateWithFlags(&e->pos_ev, cudaEventDisableTiming));
+        } else {
+            K5_CHECK_CUDA(cudaEventSynchronize(e->pos_ev));
+        }
+        std::memcpy(e->pos_pinned, text_pos, static_cast<size_t>(L) * sizeof(int));
+        K5_CHECK_CUDA(cudaMemcpyAsync(e->pos_dev + 4096, e->pos_pinned, L * sizeof(int), cudaMemcpyHostToDevice, st));
+        K5_CHECK_CUDA(cudaEventRecord(e->pos_ev, st));
         count_launch(1);
         K5_TRY(rope1d_table(e->args_text, 32, e->pos_dev + 4096, L, e->rope_t, st));
         rope_t = e->rope_t;

@@ -96,6 +96,35 @@ def test_sampler_matches_reference_golden():
     del out_host
 
 
+def test_forward_with_caller_given_text_positions():
+    """text_rope_pos that is not arange(L) (dit.py:161 hands it to RoPE1D as is): the engine stages the positions through
+    its own pinned buffer without draining the stream; checked against the oracle, called repeatedly with alternating
+    position vectors (the staging buffer is reused), and arange(L) given explicitly equals the built-in table."""
+    rec = torch.load(os.path.join(GOLD, "tiny_flash_3x16x16.pt"), weights_only=False)
+    cfg = rec["cfg"]
+    T, H, W, L = rec["T"], rec["H"], rec["W"], rec["L"]
+    model, sd = build_model(cfg, T * (H // 2) * (W // 2))
+    img, text, pooled = golden_inputs(rec)
+    x = O.model_input(img, True)
+    pos = [torch.arange(T), torch.arange(H // 2), torch.arange(W // 2)]
+    t = torch.tensor([rec["t"] * 1000.0])
+    variants = [torch.arange(L) * 3 + 5, torch.arange(L).flip(0), torch.arange(L)]
+    golds = [O.dit_forward(sd, cfg, x, text, pooled, t, pos, tp, rec["scale_factor"]) for tp in variants]
+    assert rel_l2(golds[0], golds[2]) > 4e-3 and rel_l2(golds[1], golds[2]) > 4e-3      # the positions matter (5e-3 here)
+    outs = {}
+    for rep in range(2):
+        for i, tp in enumerate(variants):
+            out = model(x.cuda(), text.cuda(), pooled.cuda(), t.cuda(), pos, tp, scale_factor=rec["scale_factor"])
+            errs = [rel_l2(out, g) for g in golds]
+            print(f"text positions variant {i} (call {rep}): engine-vs-oracle {['%.2e' % e for e in errs]}")
+            assert errs[i] < 4e-3 and errs[i] == min(errs)         # closest to the oracle run with THESE positions
+            if rep:
+                assert torch.equal(out, outs[i])
+            outs[i] = out.clone()
+    with pytest.raises(ValueError):
+        model(x.cuda(), text.cuda(), pooled.cuda(), t.cuda(), pos, torch.arange(L) + 1020, scale_factor=rec["scale_factor"])
+
+
 def test_forward_is_deterministic_and_linear_in_nothing():
     """Same inputs twice -> bit-identical outputs (no atomics / split-K on the path)."""
     rec = torch.load(os.path.join(GOLD, "tiny_flash_3x16x16.pt"), weights_only=False)
